@@ -1,0 +1,89 @@
+// common.cuh -- shared definitions of the qldpc_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/qldpc_b200.h"
+
+namespace qldpc {
+
+constexpr int kWarp = 32;
+constexpr uint16_t kPad = 0xFFFF;          // padding entry of the slot-major variable table
+constexpr int kMaxSmemPerCta = 227 * 1024; // B200: 227 KB opt-in dynamic shared memory per CTA
+
+// Device view of the graph tables.  All tables live in one uint16 blob that every CTA copies into shared
+// memory once; offsets are in uint16 units.  Edge storage is SLOT-MAJOR: the k-th edge (ascending variable)
+// of check i sits at position k*m + i, so that a warp whose lanes hold consecutive checks touches
+// consecutive shared-memory words (no bank conflicts), and -- for circulant-lifted codes -- consecutive
+// variables as well.
+struct Tables {
+    int m, n, E;
+    int dc, dv;          // max row / column weight
+    int nl;              // number of layers
+    int mw, nw;          // words(m), words(n)
+    int off_var;         // [dc*m]   variable of (slot k, check i); kPad past the end of a short row
+    int off_col_ptr;     // [n+1]
+    int off_col_pos;     // [E]      slot-major positions of the edges of variable j, ascending check
+    int off_col_chk;     // [E]      check of those edges
+    int off_layer_ptr;   // [nl+1]
+    int off_layer_chk;   // [layer_ptr[nl]]
+    int off_lvar_ptr;    // [nl+1]
+    int off_lvar_idx;    // [lvar_ptr[nl]]  sorted distinct variables adjacent to the checks of layer l
+    int len;             // blob length in uint16 units (padded to a multiple of 8)
+};
+
+struct DecodeIO {
+    const uint32_t *syn;     // [shots][mw]
+    uint32_t *ehat;          // [shots][nw]
+    int32_t *iters;          // [shots]
+    uint8_t *conv;           // [shots] or null
+    double *llr;             // [shots][n] or null
+    long long shots;
+    unsigned long long *work_counter;   // global shot dispenser (persistent CTAs pull the next shot)
+    // compacted list of unconverged shots (for OSD); null when unused
+    int *fail_count;
+    int *fail_shot;          // [fail_cap]
+    double *fail_llr;        // [fail_cap][n]
+    int fail_cap;
+};
+
+struct MsConst {
+    double L;        // prior LLR, binary64 (decoders.py:147)
+    double Lf;       // (double)(float)L : the prior as first stored into the binary32 v2c array (decoders.py:148-149)
+    double beta;     // normalisation (decoders.py:115)
+    int max_iter;
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+}  // namespace qldpc
+
+// Host-side plan object (opaque to C callers).
+struct qldpc_plan {
+    int device = 0;
+    qldpc_opts opts{};
+    qldpc::Tables tab{};
+    std::vector<uint16_t> h_blob;
+    // host copies of the graph (CSR / CSC) for the kernels that want int32 tables in global memory
+    std::vector<int32_t> row_ptr, col_idx, col_ptr, row_idx, layer_ptr, layer_chk;
+    uint16_t *d_blob = nullptr;
+    int32_t *d_row_ptr = nullptr, *d_col_idx = nullptr, *d_col_ptr = nullptr, *d_row_idx = nullptr;
+    uint32_t *d_hbits = nullptr;   // [m][nw] bit-packed rows of H (OSD, sampler, classification)
+    unsigned long long *d_work = nullptr;
+    int *d_fail_count = nullptr;
+    int sm_count = 0;
+    int rank_h = 0;                // GF(2) rank of H
+    int grid = 0, threads = 0, shots_per_cta = 0;
+    size_t smem_bytes = 0;
+    size_t state_bytes = 0;        // per-shot shared-memory state
+    // scratch for qldpc_decode_host / OSD
+    void *scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t events[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *pinned[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t pinned_bytes[4] = {0, 0, 0, 0};
+};

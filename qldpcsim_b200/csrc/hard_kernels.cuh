@@ -1,0 +1,210 @@
+// hard_kernels.cuh -- integer decoders (bit flipping, naive greedy) and the outcome classifier.
+// One warp per shot, persistent CTAs, shot state in shared memory, CSR/CSC tables read through L1.
+#pragma once
+#include "common.cuh"
+
+namespace qldpc {
+
+struct GraphDev {   // int32 CSR / CSC in global memory
+    int m, n, mw, nw;
+    const int32_t *row_ptr, *col_idx;   // CSR: variables of check i, ascending
+    const int32_t *col_ptr, *row_idx;   // CSC: checks of variable j, ascending
+};
+
+__device__ __forceinline__ uint32_t get_bit(const uint32_t *w, int i) { return (w[i >> 5] >> (i & 31)) & 1u; }
+
+// ---------------------------------------------------------------------------------------------------------
+// Parallel bit flipping -- decoders.py:74-102.
+//   nuc_j = #unsatisfied checks on j (:95); flip where nuc_j > w_j/2 (:96); the residual is
+//   (ANY flipped neighbour) xor syndrome -- an OR, not a parity (:97-98); stop when it is all-zero (:99-100).
+// Shared memory per warp: e bits [nw] | r bits [mw] | syndrome bits [mw].
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bf_decode_kernel(GraphDev g, int max_iter, DecodeIO io)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = g.nw + 2 * g.mw;
+    uint32_t *eb = reinterpret_cast<uint32_t *>(smem) + (size_t)warp * per;
+    uint32_t *rb = eb + g.nw;
+    uint32_t *sb = rb + g.mw;
+    const unsigned full = 0xffffffffu;
+    for (;;) {
+        long long shot = 0;
+        if (lane == 0) shot = (long long)atomicAdd(io.work_counter, 1ull);
+        shot = __shfl_sync(full, shot, 0);
+        if (shot >= io.shots) break;
+        for (int i = lane; i < g.nw; i += 32) eb[i] = 0u;
+        for (int i = lane; i < g.mw; i += 32) { uint32_t w = io.syn[shot * g.mw + i]; rb[i] = w; sb[i] = w; }   // r = syndrome (:90)
+        __syncwarp();
+        int iters = max_iter;
+        bool converged = false;
+        for (int it = 0; it < max_iter; ++it) {
+            for (int w = 0; w < g.nw; ++w) {                    // one word of variables per trip
+                const int j = w * 32 + lane;
+                bool flip = false;
+                if (j < g.n) {
+                    const int t0 = g.col_ptr[j], t1 = g.col_ptr[j + 1];
+                    int nuc = 0;
+                    for (int x = t0; x < t1; ++x) nuc += get_bit(rb, g.row_idx[x]);       // :95
+                    flip = 2 * nuc > (t1 - t0);                                            // nuc > nChecks/2. (:96)
+                }
+                const uint32_t fw = __ballot_sync(full, flip);
+                if (lane == 0) eb[w] ^= fw;
+            }
+            __syncwarp();
+            uint32_t any = 0;
+            for (int w = 0; w < g.mw; ++w) {
+                const int i = w * 32 + lane;
+                bool r = false;
+                if (i < g.m) {
+                    uint32_t cnt = 0;
+                    for (int x = g.row_ptr[i]; x < g.row_ptr[i + 1]; ++x) cnt |= get_bit(eb, g.col_idx[x]);   // s_hat != 0 (:97)
+                    r = (cnt ^ get_bit(sb, i)) != 0;                                                             // :98
+                }
+                const uint32_t rw = __ballot_sync(full, r);
+                if (lane == 0) rb[w] = rw;
+                any |= rw;
+            }
+            __syncwarp();
+            if (any == 0) { iters = it + 1; converged = true; break; }                     // :99-100
+        }
+        for (int w = lane; w < g.nw; w += 32) io.ehat[shot * g.nw + w] = eb[w];
+        if (lane == 0) { io.iters[shot] = iters; if (io.conv) io.conv[shot] = converged ? 1 : 0; }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Naive greedy -- decoders.py:27-66.
+//   Repeat (at most 2n times, :47): score_v = #failing checks on v (:52-56); stop if the residual is zero (:49)
+//   or the best score is 0 (:57-58); flip the LOWEST-index variable of maximal score (np.argmax, :59) and
+//   toggle its checks (:61-64).  The scores are maintained incrementally (a toggled check adds +-1 to its
+//   variables), which yields the same integers as the reference's recomputation.
+// Shared memory per warp: est bits [nw] | residual bits [mw] | score int32 [n].
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ng_decode_kernel(GraphDev g, DecodeIO io)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = g.nw + g.mw + g.n;
+    uint32_t *eb = reinterpret_cast<uint32_t *>(smem) + (size_t)warp * per;
+    uint32_t *rb = eb + g.nw;
+    int *score = reinterpret_cast<int *>(rb + g.mw);
+    const unsigned full = 0xffffffffu;
+    for (;;) {
+        long long shot = 0;
+        if (lane == 0) shot = (long long)atomicAdd(io.work_counter, 1ull);
+        shot = __shfl_sync(full, shot, 0);
+        if (shot >= io.shots) break;
+        for (int i = lane; i < g.nw; i += 32) eb[i] = 0u;
+        int rsum = 0;
+        for (int i = lane; i < g.mw; i += 32) { uint32_t w = io.syn[shot * g.mw + i]; rb[i] = w; rsum += __popc(w); }
+        rsum = __reduce_add_sync(full, rsum);
+        __syncwarp();
+        for (int j = lane; j < g.n; j += 32) {
+            int sc = 0;
+            for (int x = g.col_ptr[j]; x < g.col_ptr[j + 1]; ++x) sc += get_bit(rb, g.row_idx[x]);
+            score[j] = sc;
+        }
+        __syncwarp();
+        int steps = 0;
+        const int max_steps = 2 * g.n;                                   // :47
+        while (rsum > 0 && steps < max_steps) {                          // :49
+            ++steps;
+            int best = 0, arg = 0x7fffffff;
+            for (int j = lane; j < g.n; j += 32) {                       // ascending j per lane: strict > keeps the first
+                const int sc = score[j];
+                if (sc > best) { best = sc; arg = j; }
+            }
+            const int wbest = __reduce_max_sync(full, best);
+            if (wbest == 0) break;                                       // :57-58
+            const int v = __reduce_min_sync(full, best == wbest ? arg : 0x7fffffff);   // first maximum (:59)
+            if (lane == 0) eb[v >> 5] ^= 1u << (v & 31);                 // :61
+            const int t0 = g.col_ptr[v], t1 = g.col_ptr[v + 1];
+            for (int x = t0; x < t1; ++x) {                              // :63-64, one check at a time
+                const int ch = g.row_idx[x];
+                const int was = get_bit(rb, ch);
+                const int delta = was ? -1 : 1;
+                __syncwarp();
+                if (lane == 0) rb[ch >> 5] ^= 1u << (ch & 31);
+                for (int y = g.row_ptr[ch] + lane; y < g.row_ptr[ch + 1]; y += 32) score[g.col_idx[y]] += delta;
+                rsum += delta;
+                __syncwarp();
+            }
+        }
+        for (int w = lane; w < g.nw; w += 32) io.ehat[shot * g.nw + w] = eb[w];
+        if (lane == 0) { io.iters[shot] = steps; if (io.conv) io.conv[shot] = (rsum == 0) ? 1 : 0; }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Outcome classification + counter reduction -- simulator.py:291-303.
+//   exact : errX == eX and errZ == eZ (:294-295)
+//   degen : not exact and Hz (errX^eX) == 0 and Hx (errZ^eZ) == 0 as INTEGER products, i.e. the difference
+//           touches no check at all (:296-298, no mod 2) <=> diff & colmask == 0, colmask = OR of the rows
+//   failX : sy_z != Hz eX mod 2 (:300-301),  failZ : sy_x != Hx eZ mod 2 (:302-303)
+// One warp per shot (grid-stride); counters accumulated per CTA then atomically into int64[8].
+// ---------------------------------------------------------------------------------------------------------
+struct ClassifyArgs {
+    GraphDev gz, gx;                       // gz = Hz (X-error decode), gx = Hx (Z-error decode)
+    const uint32_t *colmask_z, *colmask_x; // [nw] OR of the rows of Hz / Hx
+    const uint32_t *errx, *errz, *ehx, *ehz, *synz, *synx;
+    const int32_t *itx, *itz;
+    long long shots;
+    unsigned long long *counters;
+};
+
+__device__ __forceinline__ bool syndrome_mismatch(const GraphDev &g, const uint32_t *e /*global [nw]*/,
+                                                  const uint32_t *syn /*global [mw]*/, int lane)
+{
+    bool bad = false;
+    for (int i = lane; i < g.m; i += 32) {
+        uint32_t par = 0;
+        for (int x = g.row_ptr[i]; x < g.row_ptr[i + 1]; ++x) par ^= get_bit(e, g.col_idx[x]);
+        bad |= par != get_bit(syn, i);
+    }
+    return __any_sync(0xffffffffu, bad);
+}
+
+__global__ void __launch_bounds__(256) classify_kernel(ClassifyArgs a)
+{
+    __shared__ unsigned long long cta_cnt[QLDPC_NUM_COUNTERS];
+    if (threadIdx.x < QLDPC_NUM_COUNTERS) cta_cnt[threadIdx.x] = 0ull;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int nw = a.gz.nw;
+    unsigned long long c_fx = 0, c_fz = 0, c_ex = 0, c_dg = 0, c_ix = 0, c_iz = 0, c_sh = 0;
+    for (long long s = warp_global; s < a.shots; s += nwarps) {
+        const uint32_t *ex = a.errx + s * nw, *ez = a.errz + s * nw, *hx = a.ehx + s * nw, *hz = a.ehz + s * nw;
+        bool diff = false, touch = false;
+        for (int w = lane; w < nw; w += 32) {
+            const uint32_t dx = ex[w] ^ hx[w], dz = ez[w] ^ hz[w];
+            diff |= (dx | dz) != 0;
+            touch |= ((dx & a.colmask_z[w]) | (dz & a.colmask_x[w])) != 0;
+        }
+        const bool exact = !__any_sync(0xffffffffu, diff);
+        const bool degen = !exact && !__any_sync(0xffffffffu, touch);
+        const bool fx = syndrome_mismatch(a.gz, hx, a.synz + s * a.gz.mw, lane);
+        const bool fz = syndrome_mismatch(a.gx, hz, a.synx + s * a.gx.mw, lane);
+        if (lane == 0) {
+            c_fx += fx; c_fz += fz; c_ex += exact; c_dg += degen;
+            c_ix += (unsigned long long)a.itx[s]; c_iz += (unsigned long long)a.itz[s]; c_sh += 1;
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(&cta_cnt[QLDPC_CNT_FAIL_X], c_fx);
+        atomicAdd(&cta_cnt[QLDPC_CNT_FAIL_Z], c_fz);
+        atomicAdd(&cta_cnt[QLDPC_CNT_EXACT], c_ex);
+        atomicAdd(&cta_cnt[QLDPC_CNT_DEGEN], c_dg);
+        atomicAdd(&cta_cnt[QLDPC_CNT_ITERS_X], c_ix);
+        atomicAdd(&cta_cnt[QLDPC_CNT_ITERS_Z], c_iz);
+        atomicAdd(&cta_cnt[QLDPC_CNT_SHOTS], c_sh);
+    }
+    __syncthreads();
+    if (threadIdx.x < QLDPC_NUM_COUNTERS && cta_cnt[threadIdx.x]) atomicAdd(&a.counters[threadIdx.x], cta_cnt[threadIdx.x]);
+}
+
+}  // namespace qldpc

@@ -1,0 +1,543 @@
+// qldpc_api.cu -- C-ABI of libqldpc_b200.so (see include/qldpc_b200.h): plan builder and launchers.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "bp_kernel.cuh"
+#include "common.cuh"
+#include "hard_kernels.cuh"
+#include "ms_kernel.cuh"
+#include "osd_kernel.cuh"
+#include "sampler_kernel.cuh"
+
+using namespace qldpc;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return fail(QLDPC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+    } while (0)
+
+template <typename T>
+int upload(T **dst, const std::vector<T> &src)
+{
+    size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
+    CU_TRY(cudaMalloc((void **)dst, bytes));
+    if (!src.empty()) CU_TRY(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int ensure_scratch(qldpc_plan *p, int slot, size_t bytes)
+{
+    if (p->scratch_bytes[slot] >= bytes) return 0;
+    if (p->scratch[slot]) cudaFree(p->scratch[slot]);
+    p->scratch[slot] = nullptr;
+    p->scratch_bytes[slot] = 0;
+    CU_TRY(cudaMalloc(&p->scratch[slot], bytes));
+    p->scratch_bytes[slot] = bytes;
+    return 0;
+}
+
+GraphDev graph_dev(const qldpc_plan *p)
+{
+    GraphDev g;
+    g.m = p->tab.m; g.n = p->tab.n; g.mw = p->tab.mw; g.nw = p->tab.nw;
+    g.row_ptr = p->d_row_ptr; g.col_idx = p->d_col_idx; g.col_ptr = p->d_col_ptr; g.row_idx = p->d_row_idx;
+    return g;
+}
+
+// ---- min-sum kernel dispatch on (max row weight, regular rows)
+typedef void (*ms_kernel_t)(Tables, const uint16_t *, MsConst, DecodeIO);
+
+template <int DC>
+ms_kernel_t ms_pick(bool regular)
+{
+    return regular ? (ms_kernel_t)ms_decode_kernel<DC, true> : (ms_kernel_t)ms_decode_kernel<DC, false>;
+}
+
+ms_kernel_t ms_select(int dc, bool regular, int *dc_inst)
+{
+    static const int sizes[] = {4, 7, 8, 12, 18, 24, 32};
+    int pick = 0;
+    for (int s : sizes) if (!pick && s >= dc) pick = s;
+    *dc_inst = pick;
+    const bool reg = regular && pick == dc;
+    switch (pick) {
+    case 4: return ms_pick<4>(reg);
+    case 7: return ms_pick<7>(reg);
+    case 8: return ms_pick<8>(reg);
+    case 12: return ms_pick<12>(reg);
+    case 18: return ms_pick<18>(reg);
+    case 24: return ms_pick<24>(reg);
+    case 32: return ms_pick<32>(reg);
+    }
+    return nullptr;
+}
+
+typedef void (*bp_kernel_t)(Tables, const uint16_t *, BpConst, DecodeIO);
+
+struct Geometry {
+    int grid, threads;
+    size_t smem;
+    int shots_per_cta;
+};
+
+}  // namespace
+
+// Extra per-plan state that needs the kernel types.
+struct PlanKernels {
+    ms_kernel_t ms = nullptr;
+    bp_kernel_t bp = nullptr;
+    bool regular = false;
+};
+static PlanKernels *kernels_of(qldpc_plan *p) { return reinterpret_cast<PlanKernels *>(p->scratch[7]); }
+
+extern "C" {
+
+int qldpc_abi_version(void) { return QLDPC_ABI_VERSION; }
+const char *qldpc_last_error(void) { return g_err.c_str(); }
+int qldpc_words(int32_t nbits) { return (nbits + 31) / 32; }
+int64_t qldpc_launch_count(void) { return g_launches.load(); }
+
+int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qldpc_plan **out)
+{
+    if (!g || !o || !out) return fail(QLDPC_EINVAL, "null argument");
+    *out = nullptr;
+    if (g->m <= 0 || g->n <= 0 || g->nnz < 0 || !g->row_ptr || (g->nnz && !g->col_idx)) return fail(QLDPC_EINVAL, "bad graph");
+    if (o->dec_type < QLDPC_NG || o->dec_type > QLDPC_BP) return fail(QLDPC_EINVAL, "Unrecognized decoder type.");
+    if (o->max_iter < 0) return fail(QLDPC_EINVAL, "max_iter < 0");
+    const int m = g->m, n = g->n, E = g->nnz;
+    if (g->row_ptr[0] != 0 || g->row_ptr[m] != E) return fail(QLDPC_EINVAL, "row_ptr does not span nnz");
+    const bool iterative = (o->dec_type == QLDPC_MS || o->dec_type == QLDPC_BP);
+    if (iterative && (g->n_layers <= 0 || !g->layer_ptr || !g->layer_chk))
+        return fail(QLDPC_EINVAL, "MS/BP need a layer list (the reference's layers=None default is unusable, decoders.py:144)");
+
+    qldpc_plan *p = new (std::nothrow) qldpc_plan();
+    if (!p) return fail(QLDPC_ENOMEM, "out of host memory");
+    p->device = device;
+    p->opts = *o;
+    p->row_ptr.assign(g->row_ptr, g->row_ptr + m + 1);
+    p->col_idx.assign(g->col_idx, g->col_idx + E);
+    auto bail = [&](int code, const std::string &msg) { qldpc_plan_destroy(p); return fail(code, msg); };
+
+    // ---- validate CSR, build CSC (ascending check per variable because rows are visited in order)
+    int dc = 0;
+    std::vector<int> cw(n, 0);
+    for (int i = 0; i < m; ++i) {
+        const int a = p->row_ptr[i], b = p->row_ptr[i + 1];
+        if (b < a) return bail(QLDPC_EINVAL, "row_ptr not monotone");
+        dc = std::max(dc, b - a);
+        for (int x = a; x < b; ++x) {
+            const int j = p->col_idx[x];
+            if (j < 0 || j >= n || (x > a && j <= p->col_idx[x - 1])) return bail(QLDPC_EINVAL, "col_idx must be ascending within a row and < n");
+            cw[j]++;
+        }
+    }
+    p->col_ptr.assign(n + 1, 0);
+    for (int j = 0; j < n; ++j) p->col_ptr[j + 1] = p->col_ptr[j] + cw[j];
+    const int dv = n ? *std::max_element(cw.begin(), cw.end()) : 0;
+    p->row_idx.assign(E, 0);
+    std::vector<int> col_slot(E, 0);   // slot (position in its row) of each CSC entry
+    {
+        std::vector<int> fill(n, 0);
+        for (int i = 0; i < m; ++i)
+            for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x) {
+                const int j = p->col_idx[x];
+                const int t = p->col_ptr[j] + fill[j]++;
+                p->row_idx[t] = i;
+                col_slot[t] = x - p->row_ptr[i];
+            }
+    }
+    bool regular = true;
+    for (int i = 0; i < m; ++i) regular = regular && (p->row_ptr[i + 1] - p->row_ptr[i] == dc);
+
+    // ---- layers
+    int nl = 0;
+    if (iterative) {
+        nl = g->n_layers;
+        p->layer_ptr.assign(g->layer_ptr, g->layer_ptr + nl + 1);
+        if (p->layer_ptr[0] != 0) return bail(QLDPC_EINVAL, "layer_ptr[0] != 0");
+        for (int l = 0; l < nl; ++l) if (p->layer_ptr[l + 1] < p->layer_ptr[l]) return bail(QLDPC_EINVAL, "layer_ptr not monotone");
+        p->layer_chk.assign(g->layer_chk, g->layer_chk + p->layer_ptr[nl]);
+        for (int c : p->layer_chk) if (c < 0 || c >= m) return bail(QLDPC_EINVAL, "layer check index out of range (the reference raises IndexError)");
+    } else {
+        p->layer_ptr.assign(1, 0);
+    }
+
+    Tables &t = p->tab;
+    t.m = m; t.n = n; t.E = E; t.dc = dc; t.dv = dv; t.nl = nl;
+    t.mw = (m + 31) / 32; t.nw = (n + 31) / 32;
+
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    p->sm_count = prop.multiProcessorCount;
+
+    // ---- device copies of CSR / CSC and bit-packed rows
+    int rc = 0;
+    if ((rc = upload(&p->d_row_ptr, p->row_ptr)) || (rc = upload(&p->d_col_idx, p->col_idx)) ||
+        (rc = upload(&p->d_col_ptr, p->col_ptr)) || (rc = upload(&p->d_row_idx, p->row_idx))) { qldpc_plan_destroy(p); return rc; }
+    {
+        std::vector<uint32_t> hb((size_t)(m + 1) * t.nw, 0u);     // row m = OR of all rows (column mask)
+        for (int i = 0; i < m; ++i)
+            for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x) {
+                const int j = p->col_idx[x];
+                hb[(size_t)i * t.nw + (j >> 5)] |= 1u << (j & 31);
+                hb[(size_t)m * t.nw + (j >> 5)] |= 1u << (j & 31);
+            }
+        if ((rc = upload(&p->d_hbits, hb))) { qldpc_plan_destroy(p); return rc; }
+        // GF(2) rank of H (gf2math.py:91-135) by bit-packed elimination on the host; OSD stops its column walk there
+        std::vector<uint32_t> w(hb.begin(), hb.begin() + (size_t)m * t.nw);
+        int r = 0;
+        for (int col = 0; col < n && r < m; ++col) {
+            const int cw = col >> 5; const uint32_t cb = 1u << (col & 31);
+            int piv = -1;
+            for (int i = r; i < m; ++i) if (w[(size_t)i * t.nw + cw] & cb) { piv = i; break; }
+            if (piv < 0) continue;
+            if (piv != r) for (int x = 0; x < t.nw; ++x) std::swap(w[(size_t)r * t.nw + x], w[(size_t)piv * t.nw + x]);
+            for (int i = r + 1; i < m; ++i)
+                if (w[(size_t)i * t.nw + cw] & cb) for (int x = 0; x < t.nw; ++x) w[(size_t)i * t.nw + x] ^= w[(size_t)r * t.nw + x];
+            ++r;
+        }
+        p->rank_h = r;
+    }
+    CU_TRY(cudaMalloc((void **)&p->d_work, 4 * sizeof(unsigned long long)));
+    CU_TRY(cudaMalloc((void **)&p->d_fail_count, 4 * sizeof(int)));
+    for (int s = 0; s < 3; ++s) CU_TRY(cudaStreamCreateWithFlags(&p->streams[s], cudaStreamNonBlocking));
+    for (int e = 0; e < 8; ++e) CU_TRY(cudaEventCreateWithFlags(&p->events[e], cudaEventDisableTiming));
+    PlanKernels *pk = new PlanKernels();
+    pk->regular = regular;
+    p->scratch[7] = pk;   // host object, slot 7 is never cudaFree'd (scratch_bytes[7] stays 0)
+
+    // ---- launch geometry
+    if (iterative) {
+        if ((long long)dc * m > 65535 || n >= 65535 || p->layer_ptr[nl] > 65535 || dc > 32)
+            return bail(QLDPC_ETOOBIG, "code too large for the on-chip decoder tables (need m*row_weight <= 65535, n < 65535, row weight <= 32)");
+        // blob
+        std::vector<uint16_t> &b = p->h_blob;
+        auto put = [&](int count) { int off = (int)b.size(); b.resize(b.size() + count, 0); return off; };
+        t.off_var = put(dc * m);
+        std::fill(b.begin() + t.off_var, b.begin() + t.off_var + dc * m, kPad);
+        for (int i = 0; i < m; ++i)
+            for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x) b[t.off_var + (x - p->row_ptr[i]) * m + i] = (uint16_t)p->col_idx[x];
+        t.off_col_ptr = put(n + 1);
+        for (int j = 0; j <= n; ++j) b[t.off_col_ptr + j] = (uint16_t)p->col_ptr[j];
+        t.off_col_pos = put(E);
+        t.off_col_chk = put(E);
+        for (int x = 0; x < E; ++x) {
+            b[t.off_col_pos + x] = (uint16_t)(col_slot[x] * m + p->row_idx[x]);
+            b[t.off_col_chk + x] = (uint16_t)p->row_idx[x];
+        }
+        t.off_layer_ptr = put(nl + 1);
+        for (int l = 0; l <= nl; ++l) b[t.off_layer_ptr + l] = (uint16_t)p->layer_ptr[l];
+        t.off_layer_chk = put((int)p->layer_chk.size());
+        for (size_t x = 0; x < p->layer_chk.size(); ++x) b[t.off_layer_chk + x] = (uint16_t)p->layer_chk[x];
+        // per-layer sorted distinct variable lists
+        std::vector<int> lvar_ptr(nl + 1, 0);
+        std::vector<uint16_t> lvar;
+        std::vector<char> seen(n, 0);
+        for (int l = 0; l < nl; ++l) {
+            std::vector<int> vs;
+            for (int q = p->layer_ptr[l]; q < p->layer_ptr[l + 1]; ++q) {
+                const int i = p->layer_chk[q];
+                for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x)
+                    if (!seen[p->col_idx[x]]) { seen[p->col_idx[x]] = 1; vs.push_back(p->col_idx[x]); }
+            }
+            std::sort(vs.begin(), vs.end());
+            for (int v : vs) { seen[v] = 0; lvar.push_back((uint16_t)v); }
+            lvar_ptr[l + 1] = (int)lvar.size();
+        }
+        if (lvar.size() > 65535) return bail(QLDPC_ETOOBIG, "per-layer variable lists exceed 65535 entries");
+        t.off_lvar_ptr = put(nl + 1);
+        for (int l = 0; l <= nl; ++l) b[t.off_lvar_ptr + l] = (uint16_t)lvar_ptr[l];
+        t.off_lvar_idx = put((int)lvar.size());
+        std::copy(lvar.begin(), lvar.end(), b.begin() + t.off_lvar_idx);
+        b.resize((b.size() + 7) & ~size_t(7), 0);
+        t.len = (int)b.size();
+        if ((rc = upload(&p->d_blob, b))) { qldpc_plan_destroy(p); return rc; }
+
+        const size_t blob_bytes = ((size_t)t.len * 2 + 15) & ~size_t(15);
+        size_t state = 0;
+        const void *fn = nullptr;
+        if (o->dec_type == QLDPC_MS) {
+            state = ms_layout(t).bytes;
+            int dci = 0;
+            pk->ms = ms_select(dc, regular, &dci);
+            fn = (const void *)pk->ms;
+        } else {
+            state = bp_layout(t).bytes;
+            pk->bp = bp_decode_kernel;
+            fn = (const void *)pk->bp;
+        }
+        if (!fn) return bail(QLDPC_ETOOBIG, "row weight not supported");
+        if (blob_bytes + state > (size_t)kMaxSmemPerCta)
+            return bail(QLDPC_ETOOBIG, "decoder state of one shot does not fit in 227 KB of shared memory");
+        int warps = (int)std::min<size_t>(32, ((size_t)kMaxSmemPerCta - blob_bytes) / state);
+        p->state_bytes = state;
+        p->threads = warps * kWarp;
+        p->shots_per_cta = warps;
+        p->smem_bytes = blob_bytes + (size_t)warps * state;
+        p->grid = p->sm_count;
+        CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta));   // per function, shared by all plans
+    } else {
+        const int warps = 8;
+        size_t per = (o->dec_type == QLDPC_BF) ? (size_t)(t.nw + 2 * t.mw) * 4 : (size_t)(t.nw + t.mw + n) * 4;
+        p->state_bytes = per;
+        p->threads = warps * kWarp;
+        p->shots_per_cta = warps;
+        p->smem_bytes = per * warps;
+        if (p->smem_bytes > (size_t)kMaxSmemPerCta) return bail(QLDPC_ETOOBIG, "code too large");
+        const void *fn = (o->dec_type == QLDPC_BF) ? (const void *)bf_decode_kernel : (const void *)ng_decode_kernel;
+        CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta));
+        int per_sm = 1;
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, p->threads, p->smem_bytes));
+        p->grid = p->sm_count * std::max(1, per_sm);
+    }
+    *out = p;
+    return QLDPC_OK;
+}
+
+int qldpc_plan_destroy(qldpc_plan *p)
+{
+    if (!p) return QLDPC_OK;
+    cudaSetDevice(p->device);
+    cudaFree(p->d_blob); cudaFree(p->d_row_ptr); cudaFree(p->d_col_idx); cudaFree(p->d_col_ptr); cudaFree(p->d_row_idx);
+    cudaFree(p->d_hbits); cudaFree(p->d_work); cudaFree(p->d_fail_count);
+    for (int s = 0; s < 7; ++s) if (p->scratch[s]) cudaFree(p->scratch[s]);
+    delete kernels_of(p);
+    for (int s = 0; s < 3; ++s) if (p->streams[s]) cudaStreamDestroy(p->streams[s]);
+    for (int e = 0; e < 8; ++e) if (p->events[e]) cudaEventDestroy(p->events[e]);
+    for (int s = 0; s < 4; ++s) if (p->pinned[s]) cudaFreeHost(p->pinned[s]);
+    delete p;
+    return QLDPC_OK;
+}
+
+int64_t qldpc_plan_info(const qldpc_plan *p, int what)
+{
+    if (!p) return -1;
+    switch (what) {
+    case 0: return p->tab.m;
+    case 1: return p->tab.n;
+    case 2: return p->tab.E;
+    case 3: return p->tab.nl;
+    case 4: return p->grid;
+    case 5: return p->threads;
+    case 6: return (int64_t)p->smem_bytes;
+    case 7: return p->shots_per_cta;
+    case 8: return p->tab.dc;
+    case 9: return p->tab.dv;
+    case 10: return p->rank_h;
+    }
+    return -1;
+}
+
+// Launch one decode pass on `stream` using work-counter slot `slot` (0..3).
+static int launch_decode(qldpc_plan *p, const uint32_t *syn, int64_t shots, uint32_t *ehat, int32_t *iters, uint8_t *conv,
+                         double *llr, int *fail_count, int *fail_shot, double *fail_llr, int fail_cap, int slot, cudaStream_t st)
+{
+    if (shots == 0) return QLDPC_OK;
+    DecodeIO io;
+    io.syn = syn; io.ehat = ehat; io.iters = iters; io.conv = conv; io.llr = llr; io.shots = shots;
+    io.work_counter = p->d_work + slot;
+    io.fail_count = fail_count; io.fail_shot = fail_shot; io.fail_llr = fail_llr; io.fail_cap = fail_cap;
+    CU_TRY(cudaMemsetAsync(p->d_work + slot, 0, sizeof(unsigned long long), st));
+    const int grid = (int)std::min<int64_t>(p->grid, (shots + p->shots_per_cta - 1) / p->shots_per_cta);
+    const qldpc_opts &o = p->opts;
+    switch (o.dec_type) {
+    case QLDPC_MS: {
+        MsConst c;
+        c.L = o.prior_llr; c.Lf = (double)(float)o.prior_llr; c.beta = o.beta; c.max_iter = o.max_iter;
+        kernels_of(p)->ms<<<grid, p->threads, p->smem_bytes, st>>>(p->tab, p->d_blob, c, io);
+        break;
+    }
+    case QLDPC_BP: {
+        BpConst c;
+        c.L0 = o.prior_llr; c.eps = o.eps; c.max_iter = o.max_iter;
+        kernels_of(p)->bp<<<grid, p->threads, p->smem_bytes, st>>>(p->tab, p->d_blob, c, io);
+        break;
+    }
+    case QLDPC_BF:
+        bf_decode_kernel<<<grid, p->threads, p->smem_bytes, st>>>(graph_dev(p), o.max_iter, io);
+        break;
+    case QLDPC_NG:
+        ng_decode_kernel<<<grid, p->threads, p->smem_bytes, st>>>(graph_dev(p), io);
+        break;
+    }
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    return QLDPC_OK;
+}
+
+static int osd_on_failures(qldpc_plan *p, uint32_t *ehat, const uint32_t *syn, int64_t shots, cudaStream_t st);
+
+int qldpc_decode(qldpc_plan *p, const uint32_t *syn, int64_t shots, uint32_t *ehat, int32_t *iters, uint8_t *conv,
+                 double *llr, void *stream)
+{
+    if (!p || shots < 0 || (shots && (!syn || !ehat || !iters))) return fail(QLDPC_EINVAL, "null argument");
+    CU_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool osd = p->opts.osd_order >= 0 && p->opts.dec_type == QLDPC_MS;   // the driver never passes OSDorder to BP (simulator.py:281-282); BP plans honour it too
+    const bool osd_bp = p->opts.osd_order >= 0 && p->opts.dec_type == QLDPC_BP;
+    if (!(osd || osd_bp)) return launch_decode(p, syn, shots, ehat, iters, conv, llr, nullptr, nullptr, nullptr, 0, 0, st);
+    // With OSD the batch is processed in chunks so that the compacted LLR buffer of the unconverged shots
+    // stays bounded: chunk * n * 8 bytes.
+    const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(shots, (int64_t)(256ll << 20) / ((int64_t)p->tab.n * 8)));
+    int rc;
+    if ((rc = ensure_scratch(p, 0, (size_t)chunk * sizeof(int)))) return rc;
+    if ((rc = ensure_scratch(p, 1, (size_t)chunk * p->tab.n * sizeof(double)))) return rc;
+    for (int64_t s0 = 0; s0 < shots; s0 += chunk) {
+        const int64_t ns = std::min(chunk, shots - s0);
+        CU_TRY(cudaMemsetAsync(p->d_fail_count, 0, sizeof(int), st));
+        rc = launch_decode(p, syn + s0 * p->tab.mw, ns, ehat + s0 * p->tab.nw, iters + s0, conv ? conv + s0 : nullptr,
+                           llr ? llr + s0 * p->tab.n : nullptr, p->d_fail_count, (int *)p->scratch[0], (double *)p->scratch[1], (int)chunk, 0, st);
+        if (rc) return rc;
+        if ((rc = osd_on_failures(p, ehat + s0 * p->tab.nw, syn + s0 * p->tab.mw, ns, st))) return rc;
+    }
+    return QLDPC_OK;
+}
+
+// OSD over the compacted failure list left by the last launch_decode (scratch[0] = shot ids, scratch[1] = LLRs).
+static int osd_on_failures(qldpc_plan *p, uint32_t *ehat, const uint32_t *syn, int64_t shots, cudaStream_t st)
+{
+    OsdArgs a;
+    a.m = p->tab.m; a.n = p->tab.n; a.mw = p->tab.mw; a.nw = p->tab.nw;
+    a.hbits = p->d_hbits;
+    a.ehat = ehat; a.syn = syn;
+    a.llr = (const double *)p->scratch[1];
+    a.perm = nullptr;
+    a.shot_ids = (const int *)p->scratch[0];
+    a.count_dev = p->d_fail_count;
+    a.count = (int)shots;           // upper bound; the kernel reads the true count from count_dev
+    a.order = p->opts.osd_order;
+    a.rank_h = p->rank_h;
+    int rc = osd_launch(a, p->sm_count, st);
+    if (rc) return fail(QLDPC_ECUDA, std::string("osd launch: ") + cudaGetErrorString((cudaError_t)rc));
+    g_launches++;
+    return QLDPC_OK;
+}
+
+int qldpc_osd(qldpc_plan *p, uint32_t *ehat, const uint32_t *syn, const double *llr, const int32_t *perm, int64_t shots,
+              int32_t order, void *stream)
+{
+    if (!p || shots < 0 || (shots && (!ehat || !syn || !llr))) return fail(QLDPC_EINVAL, "null argument");
+    if (order < 0) return QLDPC_OK;
+    CU_TRY(cudaSetDevice(p->device));
+    OsdArgs a;
+    a.m = p->tab.m; a.n = p->tab.n; a.mw = p->tab.mw; a.nw = p->tab.nw;
+    a.hbits = p->d_hbits;
+    a.ehat = ehat; a.syn = syn; a.llr = llr; a.perm = perm;
+    a.shot_ids = nullptr; a.count_dev = nullptr; a.count = (int)shots; a.order = order; a.rank_h = p->rank_h;
+    if (shots == 0) return QLDPC_OK;
+    int rc = osd_launch(a, p->sm_count, (cudaStream_t)stream);
+    if (rc) return fail(QLDPC_ECUDA, std::string("osd launch: ") + cudaGetErrorString((cudaError_t)rc));
+    g_launches++;
+    return QLDPC_OK;
+}
+
+int qldpc_decode_host(qldpc_plan *p, const uint32_t *syn, int64_t shots, uint32_t *ehat, int32_t *iters, uint8_t *conv,
+                      double *llr)
+{
+    if (!p || shots < 0 || (shots && (!syn || !ehat || !iters))) return fail(QLDPC_EINVAL, "null argument");
+    CU_TRY(cudaSetDevice(p->device));
+    const Tables &t = p->tab;
+    // Two pipeline slots; slot s owns streams[s], work counter s, and one quarter-open set of device buffers.
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(shots, llr ? (1 << 15) : (1 << 18)));
+    const size_t b_syn = (size_t)chunk * t.mw * 4, b_e = (size_t)chunk * t.nw * 4, b_it = (size_t)chunk * 4, b_cv = (size_t)chunk,
+                 b_llr = llr ? (size_t)chunk * t.n * 8 : 0;
+    auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const size_t per_slot = al(b_syn) + al(b_e) + al(b_it) + al(b_cv) + al(b_llr);
+    int rc;
+    if ((rc = ensure_scratch(p, 2, per_slot * 2))) return rc;
+    const bool osd = p->opts.osd_order >= 0 && (p->opts.dec_type == QLDPC_MS || p->opts.dec_type == QLDPC_BP);
+    int64_t k = 0;
+    for (int64_t s0 = 0; s0 < shots; s0 += chunk, ++k) {
+        const int slot = (int)(k & 1);
+        const int64_t ns = std::min(chunk, shots - s0);
+        cudaStream_t st = p->streams[slot];
+        unsigned char *base = (unsigned char *)p->scratch[2] + per_slot * slot;
+        uint32_t *d_syn = (uint32_t *)base;
+        uint32_t *d_e = (uint32_t *)(base + al(b_syn));
+        int32_t *d_it = (int32_t *)(base + al(b_syn) + al(b_e));
+        uint8_t *d_cv = (uint8_t *)(base + al(b_syn) + al(b_e) + al(b_it));
+        double *d_llr = llr ? (double *)(base + al(b_syn) + al(b_e) + al(b_it) + al(b_cv)) : nullptr;
+        // the slot's buffers are free once its previous chunk has been copied back (stream order guarantees it)
+        CU_TRY(cudaMemcpyAsync(d_syn, syn + s0 * t.mw, (size_t)ns * t.mw * 4, cudaMemcpyHostToDevice, st));
+        if (osd) {
+            // OSD path shares scratch[0..1] and the failure counter: run those chunks through the synchronous API
+            CU_TRY(cudaStreamSynchronize(p->streams[slot ^ 1]));
+            if ((rc = qldpc_decode(p, d_syn, ns, d_e, d_it, d_cv, d_llr, st))) return rc;
+        } else {
+            if ((rc = launch_decode(p, d_syn, ns, d_e, d_it, d_cv, d_llr, nullptr, nullptr, nullptr, 0, slot, st))) return rc;
+        }
+        CU_TRY(cudaMemcpyAsync(ehat + s0 * t.nw, d_e, (size_t)ns * t.nw * 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(iters + s0, d_it, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
+        if (conv) CU_TRY(cudaMemcpyAsync(conv + s0, d_cv, (size_t)ns, cudaMemcpyDeviceToHost, st));
+        if (llr) CU_TRY(cudaMemcpyAsync(llr + s0 * t.n, d_llr, (size_t)ns * t.n * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(cudaStreamSynchronize(p->streams[0]));
+    CU_TRY(cudaStreamSynchronize(p->streams[1]));
+    return QLDPC_OK;
+}
+
+int qldpc_classify(const qldpc_plan *px, const qldpc_plan *pz, const uint32_t *errx, const uint32_t *errz, const uint32_t *ehx,
+                   const uint32_t *ehz, const uint32_t *synz, const uint32_t *synx, const int32_t *itx, const int32_t *itz,
+                   int64_t shots, int64_t *counters, void *stream)
+{
+    if (!px || !pz || !counters || shots < 0) return fail(QLDPC_EINVAL, "null argument");
+    if (px->tab.n != pz->tab.n) return fail(QLDPC_EINVAL, "Hx and Hz must have the same number of columns (physical qubits).");
+    if (shots == 0) return QLDPC_OK;
+    if (!errx || !errz || !ehx || !ehz || !synz || !synx || !itx || !itz) return fail(QLDPC_EINVAL, "null argument");
+    CU_TRY(cudaSetDevice(px->device));
+    ClassifyArgs a;
+    a.gz = graph_dev(px); a.gx = graph_dev(pz);
+    a.colmask_z = px->d_hbits + (size_t)px->tab.m * px->tab.nw;
+    a.colmask_x = pz->d_hbits + (size_t)pz->tab.m * pz->tab.nw;
+    a.errx = errx; a.errz = errz; a.ehx = ehx; a.ehz = ehz; a.synz = synz; a.synx = synx; a.itx = itx; a.itz = itz;
+    a.shots = shots;
+    a.counters = reinterpret_cast<unsigned long long *>(counters);
+    const int threads = 256;
+    const int grid = (int)std::min<int64_t>((int64_t)px->sm_count * 8, (shots + 7) / 8);
+    classify_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(a);
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    return QLDPC_OK;
+}
+
+int qldpc_sample(const qldpc_plan *px, const qldpc_plan *pz, double prob, uint64_t seed, int64_t first_shot, int64_t shots,
+                 uint32_t *errx, uint32_t *errz, uint32_t *synz, uint32_t *synx, void *stream)
+{
+    if (!px || !pz || shots < 0) return fail(QLDPC_EINVAL, "null argument");
+    if (px->tab.n != pz->tab.n) return fail(QLDPC_EINVAL, "Hx and Hz must have the same number of columns (physical qubits).");
+    if (!(prob >= 0.0 && prob <= 1.0)) return fail(QLDPC_EINVAL, "p must lie in [0, 1]");
+    if (shots == 0) return QLDPC_OK;
+    if (!errx || !errz || !synz || !synx) return fail(QLDPC_EINVAL, "null argument");
+    CU_TRY(cudaSetDevice(px->device));
+    SampleArgs a;
+    a.gz = graph_dev(px); a.gx = graph_dev(pz);
+    a.p = prob; a.seed = seed; a.first_shot = first_shot; a.shots = shots;
+    a.errx = errx; a.errz = errz; a.synz = synz; a.synx = synx;
+    const int threads = 256;
+    const int grid = (int)std::min<int64_t>((int64_t)px->sm_count * 8, (shots + 7) / 8);
+    const size_t smem = (size_t)(threads / 32) * 2 * a.gz.nw * 4;
+    sample_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    return QLDPC_OK;
+}
+
+}  // extern "C"

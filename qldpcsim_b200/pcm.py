@@ -1,0 +1,146 @@
+"""
+PCM compiler (host side): dense parity-check matrix -> what the CUDA library's plan builder consumes.
+
+ * `load_matrix`     : the reference's input format (simulator.py:20-35): .npy or whitespace text, reduced
+                       mod 2, int8.
+ * `compile_pcm`     : CSR edge list in np.where(H) order (ascending check, then ascending variable --
+                       decoders.py:224), CSC, degree statistics, quasi-cyclic structure if present.
+ * `layerize`        : the check partition of the layered / serial schedules (simulator.py:212-224).
+ * `schedule_layers` : (layersX, layersZ) as the driver builds them (simulator.py:228-236).
+ * `detect_qc`       : recovers (L, base shift matrix) of a circulant-permutation lifted matrix
+                       (PCMlibrary.py:129-138, 195-201) so kernels may replace index loads by arithmetic.
+The device-side tables (slot-major edge layout, per-layer variable lists) are derived from the CSR + layers by
+qldpc_plan_create in csrc/ (see include/qldpc_b200.h).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def load_matrix(path: str) -> np.ndarray:
+    """Binary matrix from .npy or whitespace-separated 0/1 text; returns (mat % 2) as int8 (simulator.py:20-35)."""
+    if path.endswith(".npy"):
+        mat = np.load(path)
+    else:
+        rows = []
+        with open(path, "rt") as f:
+            for line in f:
+                line = line.strip()
+                if line:
+                    rows.append([int(tok) for tok in line.split()])
+        mat = np.array(rows, dtype=int)
+    return (mat % 2).astype(np.int8)
+
+
+@dataclass
+class QCInfo:
+    L: int
+    base: np.ndarray        # (m/L, n/L) int32 shifts in [0, L), -1 = zero block
+
+
+@dataclass
+class CompiledPCM:
+    H: np.ndarray           # int8 dense 0/1
+    m: int
+    n: int
+    nnz: int
+    row_ptr: np.ndarray     # int32 (m+1)
+    col_idx: np.ndarray     # int32 (nnz)   CSR
+    col_ptr: np.ndarray     # int32 (n+1)
+    row_idx: np.ndarray     # int32 (nnz)   CSC, ascending check per variable
+    row_weight_max: int
+    col_weight_max: int
+    qc: Optional[QCInfo] = None
+    _cache: dict = field(default_factory=dict, repr=False)
+
+
+def detect_qc(H: np.ndarray, candidates: Optional[Sequence[int]] = None) -> Optional[QCInfo]:
+    """Largest L > 1 for which every L x L block of H is zero or a cyclic shift of the identity."""
+    H = np.asarray(H)
+    m, n = H.shape
+    if candidates is None:
+        g = int(np.gcd(m, n))
+        candidates = [L for L in range(g, 1, -1) if g % L == 0]
+    for L in candidates:
+        if L <= 1 or m % L or n % L:
+            continue
+        mb, nb = m // L, n // L
+        blocks = H.reshape(mb, L, nb, L).transpose(0, 2, 1, 3)        # (mb, nb, L, L)
+        first = blocks[:, :, 0, :]                                     # first row of each block
+        wt = first.sum(axis=-1)
+        if (wt > 1).any():
+            continue
+        shift = np.where(wt == 1, first.argmax(axis=-1), -1).astype(np.int32)
+        r = np.arange(L)
+        cols = (r[None, None, :] + np.maximum(shift, 0)[:, :, None]) % L
+        expect = np.zeros_like(blocks)
+        bi, bj = np.nonzero(shift >= 0)
+        for i, j in zip(bi, bj):
+            expect[i, j, r, cols[i, j]] = 1
+        if np.array_equal(expect, blocks):
+            return QCInfo(L=int(L), base=shift)
+    return None
+
+
+def compile_pcm(H: np.ndarray, find_qc: bool = True) -> CompiledPCM:
+    H = (np.asarray(H) % 2).astype(np.int8)
+    if H.ndim != 2:
+        raise ValueError("parity-check matrix must be 2-D")
+    m, n = H.shape
+    chk, var = np.nonzero(H)                                 # row-major: the reference's edge order
+    nnz = int(chk.size)
+    row_ptr = np.zeros(m + 1, dtype=np.int32)
+    np.cumsum(np.bincount(chk, minlength=m), out=row_ptr[1:])
+    order = np.lexsort((chk, var))                           # by variable, then check
+    col_ptr = np.zeros(n + 1, dtype=np.int32)
+    np.cumsum(np.bincount(var, minlength=n), out=col_ptr[1:])
+    rw = np.diff(row_ptr)
+    cw = np.diff(col_ptr)
+    return CompiledPCM(H=H, m=m, n=n, nnz=nnz, row_ptr=row_ptr, col_idx=var.astype(np.int32),
+                       col_ptr=col_ptr, row_idx=chk[order].astype(np.int32),
+                       row_weight_max=int(rw.max(initial=0)), col_weight_max=int(cw.max(initial=0)),
+                       qc=detect_qc(H) if (find_qc and nnz) else None)
+
+
+def layerize(H: np.ndarray, serial: bool = False) -> List[np.ndarray]:
+    """Greedy partition of the checks into runs of consecutive rows with pairwise disjoint supports
+    (single rows when `serial`) -- the layers of simulator.py:212-224.
+
+    A run is extended row by row; the row that would give some column a second 1 starts the next run."""
+    H = np.asarray(H)
+    m = H.shape[0]
+    support = H != 0
+    cuts = [0]
+    used = np.zeros(H.shape[1], dtype=bool)
+    for i in range(m):
+        row = support[i]
+        if i > cuts[-1] and (serial or (used & row).any()):
+            cuts.append(i)
+            used = row.copy()
+        else:
+            used |= row
+    cuts.append(m)
+    return [np.arange(a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+
+
+def schedule_layers(Hx: np.ndarray, Hz: np.ndarray, decSchedule: str) -> Tuple[List[np.ndarray], List[np.ndarray]]:
+    """(layersX, layersZ) as simulator.py:228-236: 'F' one layer with every check, 'L' layerize, 'S' serial."""
+    if decSchedule == "F":
+        return [np.arange(Hx.shape[0])], [np.arange(Hz.shape[0])]
+    if decSchedule in ("L", "S"):
+        s = decSchedule == "S"
+        return layerize(Hx, serial=s), layerize(Hz, serial=s)
+    raise ValueError("Unrecognized decoder scheduling option.")
+
+
+def flatten_layers(layers: Sequence[np.ndarray]) -> Tuple[np.ndarray, np.ndarray]:
+    ptr = np.zeros(len(layers) + 1, dtype=np.int32)
+    if len(layers):
+        ptr[1:] = np.cumsum([len(l) for l in layers])
+        idx = np.concatenate([np.asarray(l, dtype=np.int32).ravel() for l in layers]).astype(np.int32)
+    else:
+        idx = np.zeros(0, dtype=np.int32)
+    return ptr, np.ascontiguousarray(idx)

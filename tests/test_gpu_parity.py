@@ -1,0 +1,315 @@
+"""
+GPU parity tests (run on the B200 box): the CUDA decoders, called through the C ABI, against
+  (1) the golden outputs of the unmodified reference (tests/golden/*.npz), every case;
+  (2) the CPU oracle on larger seeded batches;
+  (3) size-independent properties at benchmark scale.
+Bars (BASELINE.json north_star): NG / BF / OSD / outcome counters bit-exact; MS hard decisions and iteration
+counts equal on >= 99.99 % of shots; BP on >= 99.9 % of shots.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+MS_BAR = 0.9999
+BP_BAR = 0.999
+
+
+def _decoders_for(g, cuda_device):
+    from qldpcsim_b200.decoders import Decoder
+    from qldpcsim_b200.pcm import schedule_layers
+    dt, it, osd = g["decType"], int(g["decIterations"]), int(g["OSDorder"])
+    if dt in ("MS", "BP"):
+        lX, lZ = schedule_layers(g["Hx"], g["Hz"], g["sched"])
+        kw = dict(p=float(g["p"]) / 3, max_iter=it)
+        if dt == "MS":
+            kw["OSDorder"] = osd
+        return Decoder(g["Hz"], dt, layers=lX, **kw), Decoder(g["Hx"], dt, layers=lZ, **kw)
+    if dt == "BF":
+        return Decoder(g["Hz"], "BF", max_iter=50), Decoder(g["Hx"], "BF", max_iter=50)
+    return Decoder(g["Hz"], "NG"), Decoder(g["Hx"], "NG")
+
+
+def _match_fraction(out, e_ref, it_ref):
+    same = np.all(out["e_hat"] == e_ref, axis=1) & (out["iters"] == it_ref)
+    return same.mean(), same
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "OSD" not in n])
+def test_golden_decoders(name, cuda_device):
+    g = load_golden(name)
+    dX, dZ = _decoders_for(g, cuda_device)
+    oX = dX.decode(g["sy_z"])
+    oZ = dZ.decode(g["sy_x"])
+    fx, sx = _match_fraction(oX, g["eX_ref"], g["itX"])
+    fz, sz = _match_fraction(oZ, g["eZ_ref"], g["itZ"])
+    dt = g["decType"]
+    if dt in ("NG", "BF"):
+        assert fx == 1.0 and fz == 1.0, f"{name}: integer decoder must be bit-exact ({fx}, {fz})"
+    elif dt == "MS":
+        # the arithmetic is specified to the bit, so on these small sets every shot must agree
+        assert fx == 1.0 and fz == 1.0, f"{name}: MS mismatch X {np.nonzero(~sx)[0][:5]} Z {np.nonzero(~sz)[0][:5]}"
+    else:
+        n = len(sx)
+        allowed = max(1, int(np.floor((1 - BP_BAR) * n)))       # sets are small: allow one shot
+        assert (~sx).sum() <= allowed and (~sz).sum() <= allowed, f"{name}: BP match {fx}, {fz}"
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "OSD" in n])
+def test_golden_osd(name, cuda_device):
+    """MS + OSD: bit-exact when the reference's own column order (np.argsort output, stored) is supplied;
+    with the library's stable order every tie-free shot must still be bit-exact and every shot must satisfy
+    its syndrome."""
+    import torch
+    from qldpcsim_b200 import bitpack
+    from qldpcsim_b200.decoders import Decoder
+    from qldpcsim_b200.pcm import schedule_layers
+    g = load_golden(name)
+    lX, lZ = schedule_layers(g["Hx"], g["Hz"], g["sched"])
+    it, order, p = int(g["decIterations"]), int(g["OSDorder"]), float(g["p"])
+    n = g["n"]
+    for which, (H, sy, lay, e_ref, it_ref) in enumerate(((g["Hz"], g["sy_z"], lX, g["eX_ref"], g["itX"]),
+                                                         (g["Hx"], g["sy_x"], lZ, g["eZ_ref"], g["itZ"]))):
+        # (a) plain MS, posterior out, then OSD with the reference permutation
+        d = Decoder(H, "MS", p=p / 3, max_iter=it, layers=lay, OSDorder=-1)
+        o = d.decode(sy, want_llr=True)
+        assert np.array_equal(o["iters"], it_ref)
+        sel = np.nonzero(g["osd_which"] == which)[0]
+        shots_osd = g["osd_shot"][sel]
+        assert np.array_equal(np.sort(shots_osd), np.nonzero(~o["converged"])[0]), "unconverged set differs"
+        # posterior handed to OSD must be bit-identical to the reference's (float64)
+        assert np.array_equal(o["posterior"][shots_osd], g["osd_llr"][sel])
+        e_in = bitpack.unpack_rows(g["osd_e_in"][sel], n)
+        assert np.array_equal(o["e_hat"][shots_osd], e_in)
+        dev = torch.device("cuda", d.device)
+        eb = torch.from_numpy(bitpack.pack_rows(e_in).view(np.int32)).to(dev)
+        sb = torch.from_numpy(bitpack.pack_rows(sy[shots_osd]).view(np.int32)).to(dev)
+        llr = torch.from_numpy(np.ascontiguousarray(g["osd_llr"][sel])).to(dev)
+        perm = torch.from_numpy(np.ascontiguousarray(g["osd_perm"][sel].astype(np.int32))).to(dev)
+        d.osd_packed(eb, sb, llr, order, perm)
+        got = bitpack.unpack_rows(eb.cpu().numpy().view(np.uint32), n)
+        assert np.array_equal(got, e_ref[shots_osd]), f"{name}: OSD with reference perm not bit-exact"
+        # (b) fused path, library's stable order
+        d2 = Decoder(H, "MS", p=p / 3, max_iter=it, layers=lay, OSDorder=order)
+        o2 = d2.decode(sy)
+        assert np.array_equal(o2["iters"], it_ref)
+        conv = o["converged"]
+        assert np.array_equal(o2["e_hat"][conv], e_ref[conv])
+        syn_ok = ((o2["e_hat"].astype(np.int64) @ H.T.astype(np.int64)) % 2 == sy).all(axis=1)
+        assert syn_ok.all(), "OSD output must reproduce the syndrome"
+        # tie-free shots: stable order == any order
+        for k, s in zip(sel, shots_osd):
+            sat = np.where(np.abs(g["osd_llr"][k]) < 100.0, g["osd_llr"][k], 100.0 * np.sign(g["osd_llr"][k]))
+            prob = 1. / (1. + np.exp(sat))
+            rel = np.where(prob > 0.5, prob, 1 - prob)
+            if len(np.unique(rel)) == n:
+                assert np.array_equal(o2["e_hat"][s], e_ref[s]), f"{name}: tie-free shot {s} differs"
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names()])
+def test_golden_counters(name, cuda_device):
+    """simulate_p on the stored record reproduces the reference's own simulate_p counters (where stored) and the
+    counters recomputed from the reference's per-shot outputs (all cases)."""
+    from qldpcsim_b200 import simulator
+    g = load_golden(name)
+    if "OSD" in name or g["decType"] == "BP":
+        pytest.skip("tolerance-based cases are covered per shot")
+    if g["code"] == "shor" and g["decType"] in ("MS", "BP"):
+        pytest.skip("unusable in the reference")
+    r = simulator.simulate_p(g["Hx"], g["Hz"], float(g["p"]), shots=int(g["shots"]), decType=g["decType"],
+                             decIterations=int(g["decIterations"]), decSchedule=g["sched"], OSDorder=int(g["OSDorder"]),
+                             record=g["rec"])
+    Hx, Hz = g["Hx"].astype(np.int64), g["Hz"].astype(np.int64)
+    exact = (g["eX_ref"] == g["errX"]).all(axis=1) & (g["eZ_ref"] == g["errZ"]).all(axis=1)
+    failX = (((g["eX_ref"].astype(np.int64) @ Hz.T) % 2) != g["sy_z"]).any(axis=1)
+    failZ = (((g["eZ_ref"].astype(np.int64) @ Hx.T) % 2) != g["sy_x"]).any(axis=1)
+    shots = int(g["shots"])
+    assert r["DecFailures_X"] == int(failX.sum()) and r["DecFailures_Z"] == int(failZ.sum())
+    assert r["decSuccessExact"] == int(exact.sum())
+    assert r["decSuccessDegen"] == 0
+    assert round(r["Avg_number_of_iterations_X"] * shots) == int(g["itX"].sum())
+    assert round(r["Avg_number_of_iterations_Z"] * shots) == int(g["itZ"].sum())
+    if "counters" in g:
+        c = g["counters"]
+        assert [r["DecFailures_X"], r["DecFailures_Z"], r["decSuccessExact"], r["decSuccessDegen"]] == list(c[:4])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# larger seeded batches against the CPU oracle
+# ---------------------------------------------------------------------------------------------------------
+ORACLE_CASES = [
+    # code, decType, sched, p, shots, iters
+    ("steane", "MS", "F", 0.10, 20000, 50),
+    ("LP04_0", "MS", "L", 0.05, 20000, 50),
+    ("LP04_0", "MS", "F", 0.08, 5000, 50),
+    ("LP04_0", "MS", "S", 0.05, 2000, 50),
+    ("LP118_0", "MS", "L", 0.05, 10000, 50),
+    ("LP118_0", "MS", "L", 0.10, 3000, 50),
+    ("LP118_0", "MS", "F", 0.05, 4000, 50),
+    ("LP118_2", "MS", "L", 0.05, 2000, 50),
+    ("LP118_2", "MS", "S", 0.05, 300, 50),
+    ("T", "MS", "L", 0.04, 2000, 50),
+    ("bicycle", "MS", "L", 0.03, 4000, 50),
+    ("LP04_0", "NG", "F", 0.03, 5000, 50),
+    ("LP118_0", "NG", "F", 0.02, 2000, 50),
+    ("LP04_0", "BF", "F", 0.02, 5000, 50),
+    ("LP118_0", "BF", "F", 0.02, 2000, 50),
+    ("shor", "NG", "F", 0.05, 5000, 50),
+    ("shor", "BF", "F", 0.05, 5000, 50),
+    ("LP04_0", "BP", "F", 0.05, 3000, 100),
+    ("LP04_0", "BP", "L", 0.08, 2000, 30),
+    ("LP118_0", "BP", "F", 0.05, 1500, 100),
+    ("bicycle", "BP", "F", 0.03, 1500, 50),
+]
+
+
+@pytest.mark.parametrize("code,decType,sched,p,shots,iters", ORACLE_CASES)
+def test_against_oracle(code, decType, sched, p, shots, iters, cuda_device):
+    from oracle import oracle
+    from qldpcsim_b200 import pcmlibrary, sampler, simulator
+    Hx, Hz = [(h % 2).astype(np.int8) for h in pcmlibrary.by_name(code)]
+    rec = sampler.sample_record(Hx, Hz, p, shots, seed=4321)
+    want = oracle.simulate_p(Hx, Hz, rec, p, decType=decType, decIterations=iters, decSchedule=sched, details=True)
+    got = simulator.simulate_p(Hx, Hz, p, shots=shots, decType=decType, decIterations=iters, decSchedule=sched,
+                               record=rec, details=True)
+    wd, gd = want["_details"], got["_details"]
+    n = Hx.shape[1]
+    from qldpcsim_b200 import bitpack
+    eX = bitpack.unpack_rows(gd["eX"].view(np.uint32), n)
+    eZ = bitpack.unpack_rows(gd["eZ"].view(np.uint32), n)
+    sameX = (eX == wd["eX"]).all(axis=1) & (gd["itX"] == wd["itX"])
+    sameZ = (eZ == wd["eZ"]).all(axis=1) & (gd["itZ"] == wd["itZ"])
+    if decType in ("NG", "BF"):
+        assert sameX.all() and sameZ.all()
+        for k in ("DecFailures_X", "DecFailures_Z", "decSuccessExact", "decSuccessDegen",
+                  "Avg_number_of_iterations_X", "Avg_number_of_iterations_Z"):
+            assert got[k] == want[k], k
+    elif decType == "MS":
+        assert sameX.mean() >= MS_BAR and sameZ.mean() >= MS_BAR, (sameX.mean(), sameZ.mean())
+        assert sameX.all() and sameZ.all(), "MS is specified to the bit; any mismatch is a bug"
+        for k in ("DecFailures_X", "DecFailures_Z", "decSuccessExact", "decSuccessDegen"):
+            assert got[k] == want[k], k
+    else:
+        assert sameX.mean() >= BP_BAR and sameZ.mean() >= BP_BAR, (sameX.mean(), sameZ.mean())
+        # qBLER inside the 95 % binomial interval of the oracle's
+        q_ref = 1 - want["decSuccessExact"] / shots
+        q = 1 - got["decSuccessExact"] / shots
+        half = 1.96 * np.sqrt(max(q_ref * (1 - q_ref), 1e-12) / shots) + 1.0 / shots
+        assert abs(q - q_ref) <= half
+
+
+def test_reference_signature_functions(cuda_device):
+    """The five per-shot functions keep the reference's signatures, return types and dtypes."""
+    from qldpcsim_b200 import decoders as D
+    g = load_golden("LP04_0_MS_L_p05")
+    from qldpcsim_b200.pcm import schedule_layers
+    lX, _ = schedule_layers(g["Hx"], g["Hz"], "L")
+    s = 3
+    e, it = D.MS_decoder(g["Hz"], g["sy_z"][s].astype(int), p=0.05 / 3, max_iter=50, layers=lX)
+    assert e.dtype == np.int8 and isinstance(it, int) and np.array_equal(e, g["eX_ref"][s]) and it == g["itX"][s]
+    e, it = D.BP_decoder(g["Hz"], g["sy_z"][s].astype(int), p=0.05 / 3, max_iter=50, layers=lX)
+    assert e.dtype == np.int64 and e.shape == (g["n"],)
+    e, it = D.BF_decoder(g["Hz"], g["sy_z"][s].astype(int))
+    assert e.dtype == np.bool_
+    e, it = D.NG_decoder(g["Hz"], g["sy_z"][s].astype(int))
+    assert e.dtype == np.int8
+    with pytest.raises(AttributeError):
+        D.MS_decoder(g["Hz"], g["sy_z"][s].astype(int), p=0.01)        # layers=None is unusable in the reference too
+    out = D.MS_decoder(np.zeros((0, 5)), np.zeros(0), p=0.01, layers=[])
+    assert isinstance(out, np.ndarray) and out.size == 0                # decoders.py:138-139: bare array
+
+
+def test_osddec_function(cuda_device):
+    from qldpcsim_b200 import bitpack, decoders as D
+    g = load_golden("LP04_0_MS_L_OSD0_p10")
+    k = 0
+    H = g["Hz"] if g["osd_which"][k] == 0 else g["Hx"]
+    sy = (g["sy_z"] if g["osd_which"][k] == 0 else g["sy_x"])[g["osd_shot"][k]]
+    ref = (g["eX_ref"] if g["osd_which"][k] == 0 else g["eZ_ref"])[g["osd_shot"][k]]
+    e = bitpack.unpack_rows(g["osd_e_in"][k:k + 1], g["n"])[0].astype(np.int8)
+    out = D.OSDdec(H, e, sy.astype(int), g["osd_llr"][k], 0, perm=g["osd_perm"][k])
+    assert out is e and np.array_equal(e, ref)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# device sampler and properties at scale
+# ---------------------------------------------------------------------------------------------------------
+def _philox_host(c0, c1, c2, c3, k0, k1):
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    mask = 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & mask, p1 & mask, ((p0 >> 32) ^ c3 ^ k1) & mask, p0 & mask
+        k0, k1 = (k0 + W0) & mask, (k1 + W1) & mask
+    return c0, c1, c2, c3
+
+
+def test_device_sampler_matches_host_restatement(cuda_device):
+    """qldpc_sample against a pure-Python restatement of its definition (Philox4x32-10, thresholds k p/3 2^32)."""
+    from qldpcsim_b200 import bitpack, pcmlibrary, simulator
+    Hx, Hz = pcmlibrary.by_name("LP04_0")
+    p, seed, first, shots = 0.07, 0x1234ABCD5678, 1000, 6
+    pipe = simulator.Pipeline(Hx, Hz, p, "NG")
+    synz, synx, errx, errz = [t.cpu().numpy().view(np.uint32) for t in pipe.sample_device(shots, seed, first)]
+    n = Hx.shape[1]
+    thr = [min(int((k + 1) * p / 3.0 * 4294967296.0 + 0.5), 4294967296) for k in range(3)]
+    eX = np.zeros((shots, n), np.uint8)
+    eZ = np.zeros((shots, n), np.uint8)
+    for s in range(shots):
+        gs = first + s
+        for q in range(n):
+            w, bit = q // 32, q % 32
+            r = _philox_host(gs & 0xFFFFFFFF, gs >> 32, w * 8 + bit // 4, 0, seed & 0xFFFFFFFF, seed >> 32)[bit % 4]
+            X, Y, Z = r < thr[0], thr[0] <= r < thr[1], thr[1] <= r < thr[2]
+            eX[s, q], eZ[s, q] = X or Y, Z or Y
+    assert np.array_equal(bitpack.unpack_rows(errx, n), eX) and np.array_equal(bitpack.unpack_rows(errz, n), eZ)
+    assert np.array_equal(bitpack.unpack_rows(synz, Hz.shape[0]), (eX @ Hz.T) % 2)
+    assert np.array_equal(bitpack.unpack_rows(synx, Hx.shape[0]), (eZ @ Hx.T) % 2)
+
+
+def test_device_sampler_statistics_and_sharding(cuda_device):
+    from qldpcsim_b200 import bitpack, pcmlibrary, simulator
+    Hx, Hz = pcmlibrary.by_name("LP118_0")
+    p, shots = 0.06, 200000
+    pipe = simulator.Pipeline(Hx, Hz, p, "NG")
+    full = [t.cpu().numpy() for t in pipe.sample_device(shots, 99, 0)]
+    a = [t.cpu().numpy() for t in pipe.sample_device(shots // 2, 99, 0)]
+    b = [t.cpu().numpy() for t in pipe.sample_device(shots - shots // 2, 99, shots // 2)]
+    for f, x, y in zip(full, a, b):
+        assert np.array_equal(f, np.concatenate([x, y])), "batch must not depend on the sharding"
+    n = Hx.shape[1]
+    eX = bitpack.unpack_rows(full[2].view(np.uint32), n)
+    eZ = bitpack.unpack_rows(full[3].view(np.uint32), n)
+    N = shots * n
+    for est, want in ((eX.mean(), 2 * p / 3), (eZ.mean(), 2 * p / 3), ((eX & eZ).mean(), p / 3)):
+        assert abs(est - want) < 5 * np.sqrt(want * (1 - want) / N)
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE-size batch (10^6 shots, LP118_0 MS-L 50 it): converged <=> syndrome reproduced, iteration range,
+    counters independent of chunking, exact + failures consistent."""
+    import torch
+    from qldpcsim_b200 import pcmlibrary, simulator
+    Hx, Hz = pcmlibrary.by_name("LP118_0")
+    shots, p = 1_000_000, 0.05
+    pipe = simulator.Pipeline(Hx, Hz, p, "MS", 50, "L")
+    synz, synx, errx, errz = pipe.sample_device(shots, 7, 0)
+    c1 = pipe.run(synz, synx, errx, errz, keep=True).cpu().numpy()
+    last = pipe.last
+    conv = last["convX"].bool()
+    it = last["itX"]
+    assert int(it.min()) >= 1 and int(it.max()) <= 50
+    assert bool((it[~conv] == 50).all())
+    # failures counted by the classifier (fresh syndrome computation) == unconverged shots of the decoder
+    assert c1[0] == int((~conv).sum().item()) and c1[1] == int((~last["convZ"].bool()).sum().item())
+    assert c1[6] == shots and c1[4] == int(it.sum().item())
+    # chunking invariance (what multi-GPU sharding relies on)
+    c2 = torch.zeros(8, dtype=torch.int64, device=pipe.device)
+    for lo in range(0, shots, 300_000):
+        hi = min(shots, lo + 300_000)
+        pipe.run(synz[lo:hi], synx[lo:hi], errx[lo:hi], errz[lo:hi], counters=c2)
+    assert np.array_equal(c1, c2.cpu().numpy())
+    # exact matches cannot be failures
+    assert c1[2] + max(c1[0], c1[1]) <= shots
