@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark: X+Z shots decoded per second, LP118_0 lifted-product code, normalised min-sum,
+layered schedule, 50 iterations, OSD off, depolarizing p = 0.05, 10^6 shots per step per GPU (weak scaling).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one resident batch: decode the X errors (plan on Hz), decode the Z errors
+(plan on Hx), classify + count (simulator.py:244-304 of the reference), followed by the one collective of the path,
+an all-reduce of the int64[8] counters.  Prints ONE JSON line on rank 0.
+
+  value     : shots/s with the bit-packed syndromes/errors already in HBM (device sampler, untimed), CUDA events,
+              max over ranks.
+  e2e       : same metric through the host-buffer C-ABI call (qldpc_decode_host): pinned host syndromes in,
+              error estimates + iteration counts + convergence flags back in pinned host memory, copies inside
+              the timed region.
+  roofline  : the dominant kernel (ms_decode_kernel); achieved = algorithmic bytes (16 B per edge-iteration for the
+              layered schedule, SURVEY.md section 8d, + bit-packed I/O) / its CUDA-event time, against the measured HBM copy
+              bandwidth of MEASURED_PEAKS.json.  The kernel keeps its state in shared memory, so real DRAM traffic is
+              far below the algorithmic figure; `traffic` comes from profiles/ when an ncu capture exists.
+  cpu_baseline / --impl reference : the CPU oracle (C port of the reference's decoders, OpenMP over shots) on a bounded
+              sample of the same workload on this box's host cores.  The reference itself is Python and cannot travel;
+              DESIGN.md records its own speed measured in the build container.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CODE = "LP118_0"
+P_DEPOL = 0.05
+DEC_ITERS = 50
+SCHEDULE = "L"
+SHOTS_PER_STEP = 1_000_000
+BYTES_PER_EDGE_ITER = 16.0          # layered / serial: c2v read+write, posterior read+write
+CPU_SAMPLE_SHOTS = 32768
+REF_STEP_SHOTS = 8192
+METRIC = "shots/sec decoded (X+Z), LP118_0 MS-layered 50 it"
+UNIT = "shots/s"
+
+
+def workload_name(shots):
+    return (f"{CODE} lifted-product code [[544,80]] (Hx,Hz 240x544, 1920 edges each), min-sum layered (13/11 layers), "
+            f"{DEC_ITERS} iterations, OSD off, depolarizing p={P_DEPOL}, {shots} shots per step per GPU")
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def recorded_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        try:
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            try:
+                self.proc.kill()
+            except Exception:
+                pass
+            return None
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        busy = [x for x in sm if x >= 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU oracle timing (cpu_baseline leg and --impl reference)
+# ---------------------------------------------------------------------------------------------------------
+def cpu_decode_rate(shots, seed, threads, repeat=1):
+    from oracle import oracle
+    from qldpcsim_b200 import pcmlibrary, sampler
+    Hx, Hz = [(h % 2).astype(np.int8) for h in pcmlibrary.by_name(CODE)]
+    rec = sampler.sample_record(Hx, Hz, P_DEPOL, shots, seed=seed)
+    sy_z, sy_x, _, _ = oracle.split_record(rec, Hz.shape[0], Hx.shape[0], Hx.shape[1])
+    lX, lZ = oracle.schedule_layers(Hx, Hz, SCHEDULE)
+    gz, gx = oracle.Graph(Hz), oracle.Graph(Hx)
+    times = []
+    for _ in range(repeat):
+        t0 = time.perf_counter()
+        gz.decode("MS", sy_z, p=P_DEPOL / 3, max_iter=DEC_ITERS, layers=lX, n_threads=threads)     # simulator.py:278
+        gx.decode("MS", sy_x, p=P_DEPOL / 3, max_iter=DEC_ITERS, layers=lZ, n_threads=threads)     # simulator.py:279
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    from oracle import oracle
+    oracle.build()
+    times = cpu_decode_rate(REF_STEP_SHOTS, 1234, cores, repeat=args.warmup + args.steps)[args.warmup:]
+    total = sum(times)
+    value = REF_STEP_SHOTS * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(SHOTS_PER_STEP), "reference_step": f"{REF_STEP_SHOTS} shots of that workload per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{REF_STEP_SHOTS} shots per step x {len(times)} steps, oracle/qldpc_oracle.c (C port of decoders.py "
+                                   f"MS_decoder, OpenMP over shots); the Python reference itself cannot travel to this box"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from qldpcsim_b200 import _lib, bitpack, pcmlibrary, simulator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    shots = args.shots
+    Hx, Hz = [(h % 2).astype(np.int8) for h in pcmlibrary.by_name(CODE)]
+    pipe = simulator.Pipeline(Hx, Hz, P_DEPOL, "MS", DEC_ITERS, SCHEDULE, device=local)
+    E = pipe.decX.pcm.nnz
+    n_batches = min(4, max(1, args.steps))
+    # resident synthetic batches: global shot index = (step slot * world + rank) * shots + s
+    batches = [pipe.sample_device(shots, seed=20261018, first_shot=(b * world + rank) * shots) for b in range(n_batches)]
+    torch.cuda.synchronize(dev)
+
+    lib = _lib.lib()
+    counters = torch.zeros(_lib.NUM_COUNTERS, dtype=torch.int64, device=dev)
+    nw, mzw, mxw = bitpack.words(pipe.n), bitpack.words(pipe.m_z), bitpack.words(pipe.m_x)
+    outX = (torch.empty((shots, nw), dtype=torch.int32, device=dev), torch.empty(shots, dtype=torch.int32, device=dev), None, None)
+    outZ = (torch.empty((shots, nw), dtype=torch.int32, device=dev), torch.empty(shots, dtype=torch.int32, device=dev), None, None)
+
+    def step(b, ev=None):
+        synz, synx, errx, errz = batches[b % n_batches]
+        st = torch.cuda.current_stream(dev)
+        if ev:
+            ev[0].record(st)
+        pipe.decX.decode_packed(synz, out=outX)
+        if ev:
+            ev[1].record(st)
+        pipe.decZ.decode_packed(synx, out=outZ)
+        if ev:
+            ev[2].record(st)
+        _lib.check(lib.qldpc_classify(pipe.decX.handle, pipe.decZ.handle, errx.data_ptr(), errz.data_ptr(), outX[0].data_ptr(),
+                                      outZ[0].data_ptr(), synz.data_ptr(), synx.data_ptr(), outX[1].data_ptr(), outZ[1].data_ptr(),
+                                      shots, counters.data_ptr(), st.cuda_stream))
+        if world > 1:
+            dist.all_reduce(counters)          # the path's only collective (64 bytes); counters are re-zeroed per step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for w in range(args.warmup):
+        counters.zero_()
+        step(w)
+    barrier()
+    launches0 = lib.qldpc_launch_count()
+    clk = ClockSampler(local) if rank == 0 else None
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    per_step_counters = []
+    barrier()
+    t_begin.record(torch.cuda.current_stream(dev))
+    for k in range(args.steps):
+        counters.zero_()
+        step(k, evs[k])
+        per_step_counters.append(counters.clone())
+    t_end.record(torch.cuda.current_stream(dev))
+    barrier()
+    elapsed_ms = t_begin.elapsed_time(t_end)
+    launches = lib.qldpc_launch_count() - launches0
+    clocks = clk.stop() if clk else None
+    tX = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    tZ = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    cs = torch.stack(per_step_counters).cpu().numpy().astype(np.float64)
+    # counters were all-reduced: per-rank share for the roofline (weak scaling, identical distributions)
+    itX, itZ = cs[:, _lib.CNT_ITERS_X].mean() / world, cs[:, _lib.CNT_ITERS_Z].mean() / world
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = shots * world * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- e2e: host-buffer C-ABI call, copies inside the timed region
+    hsz = torch.empty((shots, mzw), dtype=torch.int32).pin_memory()
+    hsx = torch.empty((shots, mxw), dtype=torch.int32).pin_memory()
+    hsz.copy_(batches[0][0].cpu())
+    hsx.copy_(batches[0][1].cpu())
+    h_out = [(torch.empty((shots, nw), dtype=torch.int32).pin_memory(), torch.empty(shots, dtype=torch.int32).pin_memory(),
+              torch.empty(shots, dtype=torch.uint8).pin_memory()) for _ in range(2)]
+
+    def e2e_step():
+        for (dec, hs, ho) in ((pipe.decX, hsz, h_out[0]), (pipe.decZ, hsx, h_out[1])):
+            _lib.check(lib.qldpc_decode_host(dec.handle, hs.data_ptr(), shots, ho[0].data_ptr(), ho[1].data_ptr(), ho[2].data_ptr(), None))
+
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize(dev)
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = shots * world * e2e_steps / float(te.item())
+    # e2e results must equal the device-resident results of the same batch
+    pipe.decX.decode_packed(batches[0][0], out=outX)
+    torch.cuda.synchronize(dev)
+    assert torch.equal(h_out[0][0], outX[0].cpu()) and torch.equal(h_out[0][1], outX[1].cpu()), "host path differs from device path"
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        io_bytes = shots * (4 * mzw + 4 * nw + 4) + shots * (4 * mxw + 4 * nw + 4)
+        alg_bytes = (itX + itZ) * E * BYTES_PER_EDGE_ITER + io_bytes
+        achieved = alg_bytes / ((tX + tZ) * 1e-3) / 1e9
+        tr = recorded_traffic()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(shots), "decType": "MS", "decSchedule": "L", "decIterations": DEC_ITERS, "p": P_DEPOL,
+                       "shots_per_step_per_gpu": shots, "sharding": f"shots x {world} ranks, counters all-reduced (NCCL)" if world > 1 else "single GPU",
+                       "l2": "inputs+outputs per step (~345 MB) exceed the 126 MB L2; 4 resident batches cycled",
+                       "avg_iters_X": itX / shots, "avg_iters_Z": itZ / shots,
+                       "edge_iterations_per_s": (itX + itZ) * E * world / (elapsed_ms / args.steps * 1e-3)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": shots * 4 * (mzw + mxw),
+                    "d2h_bytes_per_step": shots * 2 * (4 * nw + 4 + 1), "api": "qldpc_decode_host (pinned host buffers), X then Z"},
+            "gpu_launches": int(launches) * world,
+            "roofline": {"bound": "hbm", "kernel": "ms_decode_kernel<8,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_src,
+                         "bytes_per_edge_iteration": BYTES_PER_EDGE_ITER, "kernel_ms_per_step": tX + tZ,
+                         "kernel_share_of_step": (tX + tZ) / (elapsed_ms / args.steps),
+                         "traffic": tr.get("dram_bytes_per_launch") if tr else None},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            from oracle import oracle
+            oracle.build()
+            cores = os.cpu_count() or 1
+            tcpu = cpu_decode_rate(CPU_SAMPLE_SHOTS, 1234, cores)[0]
+            line["cpu_baseline"] = {"value": CPU_SAMPLE_SHOTS / tcpu, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{CPU_SAMPLE_SHOTS} shots of the same workload (host sampler seed 1234), "
+                                              f"oracle/qldpc_oracle.c MS decode X+Z, OpenMP {cores} threads"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shots", type=int, default=SHOTS_PER_STEP, help="shots per step per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,60 @@
+"""Live differential test of the oracle against the unmodified reference (only where /root/reference exists)."""
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import oracle, ref_loader
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present (GPU box)")
+
+CASES = [("steane", "MS", "S", 0.08, 120), ("steane", "BP", "L", 0.08, 80), ("LP04_0", "MS", "L", 0.07, 24),
+         ("LP04_0", "NG", "F", 0.03, 24), ("LP04_0", "BF", "F", 0.03, 24), ("LP04_1", "MS", "F", 0.06, 12),
+         ("bicycle", "BP", "L", 0.02, 4)]
+
+
+@pytest.mark.parametrize("code,decType,sched,p,shots", CASES)
+def test_live(code, decType, sched, p, shots):
+    from qldpcsim_b200 import pcmlibrary, sampler
+    warnings.filterwarnings("ignore")
+    dec = ref_loader.load("decoders")
+    Hx, Hz = [(h % 2).astype(np.int8) for h in pcmlibrary.by_name(code)]
+    rec = sampler.sample_record(Hx, Hz, p, shots, seed=99)
+    sy_z, sy_x, _, _ = oracle.split_record(rec, Hz.shape[0], Hx.shape[0], Hx.shape[1])
+    lX, lZ = oracle.schedule_layers(Hx, Hz, sched)
+    bad = 0
+    for H, sy, lay in ((Hz, sy_z, lX), (Hx, sy_x, lZ)):
+        kw = dict(p=p / 3, max_iter=30, layers=lay) if decType in ("MS", "BP") else {}
+        o = oracle.Graph(H).decode(decType, sy, **({"max_iter": 50} if decType == "BF" else kw))
+        for s in range(shots):
+            syn = sy[s].astype(int)
+            if decType == "NG":
+                e, i = dec.NG_decoder(H, syn)
+            elif decType == "BF":
+                e, i = dec.BF_decoder(H, syn)
+            elif decType == "MS":
+                e, i = dec.MS_decoder(H, syn, **kw)
+            else:
+                e, i = dec.BP_decoder(H, syn, **kw)
+            bad += not (np.array_equal(np.asarray(e).astype(np.uint8), o["e_hat"][s]) and i == o["iters"][s])
+    assert bad == 0
+
+
+def test_layerize_matches_reference():
+    from qldpcsim_b200 import pcm, pcmlibrary
+    ref_layerize = ref_loader.load_layerize()
+    for code in ("steane", "shor", "LP04_0", "LP118_0", "T", "bicycle"):
+        for H in pcmlibrary.by_name(code):
+            for serial in (False, True):
+                a = ref_layerize(H, serial=serial)
+                for impl in (oracle.layerize, pcm.layerize):
+                    b = impl(H, serial=serial)
+                    assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b)), (code, serial)
+
+
+def test_rank_matches_reference():
+    from qldpcsim_b200 import pcmlibrary
+    gf2 = ref_loader.load("gf2math")
+    for code in ("steane", "shor", "LP04_0"):
+        for H in pcmlibrary.by_name(code):
+            assert oracle.gf2_rank(H) == gf2.rank(H)
