@@ -113,9 +113,9 @@ __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint
                     int deg = 0;
                     for (int k = 0; k < dc; ++k) {
                         const int pos = k * m + i;
-                        const uint16_t j = var_tab[pos];
-                        if (j == kPad) break;
-                        const double v = __dsub_rn(T[j], c2v[pos]);
+                        const uint32_t joff = var_tab[pos];                      // byte offset 4*j
+                        if (joff == kPad) break;
+                        const double v = __dsub_rn(T[joff >> 2], c2v[pos]);
                         prod = __dmul_rn(prod, tanh(v / 2.0));                     // :253-254 (np.prod is sequential)
                         ++deg;
                     }
@@ -124,8 +124,7 @@ __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint
                     // position by position, after its own v2c has been rebuilt)
                     for (int k = 0; k < deg; ++k) {
                         const int pos = k * m + i;
-                        const uint16_t j = var_tab[pos];
-                        const double v = __dsub_rn(T[j], c2v[pos]);
+                        const double v = __dsub_rn(T[var_tab[pos] >> 2], c2v[pos]);
                         double th2 = prod / tanh(v / 2.0);                         // :256
                         if (fabs(th2) >= one_m_eps) {                              // :257-258
                             const double sg = (th2 > 0.0) ? 1.0 : ((th2 < 0.0) ? -1.0 : 0.0);

@@ -24,7 +24,7 @@ struct Tables {
     int dc, dv;          // max row / column weight
     int nl;              // number of layers
     int mw, nw;          // words(m), words(n)
-    int off_var;         // [dc*m]   variable of (slot k, check i); kPad past the end of a short row
+    int off_var;         // [dc*m]   BYTE offset (4*j) of the variable of (slot k, check i); kPad past the end of a short row
     int off_col_ptr;     // [n+1]
     int off_col_pos;     // [E]      slot-major positions of the edges of variable j, ascending check
     int off_col_chk;     // [E]      check of those edges
@@ -32,6 +32,12 @@ struct Tables {
     int off_layer_chk;   // [layer_ptr[nl]]
     int off_lvar_ptr;    // [nl+1]
     int off_lvar_idx;    // [lvar_ptr[nl]]  sorted distinct variables adjacent to the checks of layer l
+    int off_layer_lpc;   // [nl]     lanes per check used by the min-sum check phase in layer l (1, 2, 4 or 8)
+    int off_vn;          // [n][dvs] BYTE offsets (4*(k*m+i)) of the edges of variable j, ascending check, padded with
+                         //          the offset of the always-zero slot 4*dc*m; dvs = 4, 8 or 16 (min-sum only)
+    int off_rowpar;      // [2*mw]   parity of the row weights as bit words (low half, high half)
+    int dvs;
+    int n_pad;           // n rounded up to a multiple of 32 (first-step variable sweep)
     int len;             // blob length in uint16 units (padded to a multiple of 8)
 };
 
@@ -54,6 +60,7 @@ struct MsConst {
     double L;        // prior LLR, binary64 (decoders.py:147)
     double Lf;       // (double)(float)L : the prior as first stored into the binary32 v2c array (decoders.py:148-149)
     double beta;     // normalisation (decoders.py:115)
+    float Tf;        // -L rounded UP to binary32: fl64(L + S) < 0  <=>  S < Tf for binary32 S
     int max_iter;
 };
 
@@ -76,6 +83,7 @@ struct qldpc_plan {
     int *d_fail_count = nullptr;
     int sm_count = 0;
     int rank_h = 0;                // GF(2) rank of H
+    int row_w = 0;                 // true max row weight (tab.dc may be padded to the instantiated kernel shape)
     int grid = 0, threads = 0, shots_per_cta = 0;
     size_t smem_bytes = 0;
     size_t state_bytes = 0;        // per-shot shared-memory state

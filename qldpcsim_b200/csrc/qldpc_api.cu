@@ -61,30 +61,42 @@ GraphDev graph_dev(const qldpc_plan *p)
     return g;
 }
 
-// ---- min-sum kernel dispatch on (max row weight, regular rows)
+// ---- min-sum kernel dispatch on (max row weight, regular rows, max column weight)
 typedef void (*ms_kernel_t)(Tables, const uint16_t *, MsConst, DecodeIO);
 
-template <int DC>
+template <int DC, int DV>
 ms_kernel_t ms_pick(bool regular)
 {
-    return regular ? (ms_kernel_t)ms_decode_kernel<DC, true> : (ms_kernel_t)ms_decode_kernel<DC, false>;
+    return regular ? (ms_kernel_t)ms_decode_kernel<DC, true, DV> : (ms_kernel_t)ms_decode_kernel<DC, false, DV>;
 }
 
-ms_kernel_t ms_select(int dc, bool regular, int *dc_inst)
+template <int DC>
+ms_kernel_t ms_pick_dv(int dv_inst, bool regular)
 {
-    static const int sizes[] = {4, 7, 8, 12, 18, 24, 32};
-    int pick = 0;
-    for (int s : sizes) if (!pick && s >= dc) pick = s;
-    *dc_inst = pick;
-    const bool reg = regular && pick == dc;
-    switch (pick) {
-    case 4: return ms_pick<4>(reg);
-    case 7: return ms_pick<7>(reg);
-    case 8: return ms_pick<8>(reg);
-    case 12: return ms_pick<12>(reg);
-    case 18: return ms_pick<18>(reg);
-    case 24: return ms_pick<24>(reg);
-    case 32: return ms_pick<32>(reg);
+    switch (dv_inst) {
+    case 4: return ms_pick<DC, 4>(regular);
+    case 5: return ms_pick<DC, 5>(regular);
+    case 9: return ms_pick<DC, 9>(regular);
+    case 16: return ms_pick<DC, 16>(regular);
+    }
+    return nullptr;
+}
+
+// Instantiated shapes: row weight <= 4 / 8 / 18 / 32, column weight <= 4 / 5 / 9 / 16.
+ms_kernel_t ms_select(int dc, int dv, bool regular, int *dc_inst, int *dv_inst)
+{
+    static const int dcs[] = {4, 8, 18, 32}, dvs[] = {4, 5, 9, 16};
+    int pc = 0, pv = 0;
+    for (int s : dcs) if (!pc && s >= dc) pc = s;
+    for (int s : dvs) if (!pv && s >= dv) pv = s;
+    *dc_inst = pc; *dv_inst = pv;
+    if (!pc || !pv) return nullptr;
+    const bool reg = regular && pc == dc;
+    switch (pc) {
+    case 4: return ms_pick_dv<4>(pv, reg);
+    case 8: return ms_pick_dv<8>(pv, reg);
+    case 18: return ms_pick_dv<18>(pv, reg);
+    case 32: return ms_pick_dv<32>(pv, reg);
     }
     return nullptr;
 }
@@ -181,6 +193,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
 
     Tables &t = p->tab;
     t.m = m; t.n = n; t.E = E; t.dc = dc; t.dv = dv; t.nl = nl;
+    p->row_w = dc;
     t.mw = (m + 31) / 32; t.nw = (n + 31) / 32;
 
     CU_TRY(cudaSetDevice(device));
@@ -231,10 +244,20 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
         // blob
         std::vector<uint16_t> &b = p->h_blob;
         auto put = [&](int count) { int off = (int)b.size(); b.resize(b.size() + count, 0); return off; };
+        const bool is_ms = o->dec_type == QLDPC_MS;
+        int dc_inst = 0, dv_inst = 0;
+        if (is_ms) {
+            pk->ms = ms_select(dc, dv, regular, &dc_inst, &dv_inst);
+            if (!pk->ms) return bail(QLDPC_ETOOBIG, "min-sum kernels are instantiated for row weight <= 32 and column weight <= 16");
+            dc = dc_inst;              // slot-major tables are padded to the instantiated row weight
+            t.dc = dc;
+            if ((long long)dc * m * 4 + 4 > 65535 || (long long)n * 4 > 65535)
+                return bail(QLDPC_ETOOBIG, "code too large for the 16-bit shared-memory offset tables (need 4*m*row_weight < 65532, 4*n < 65536)");
+        }
         t.off_var = put(dc * m);
         std::fill(b.begin() + t.off_var, b.begin() + t.off_var + dc * m, kPad);
         for (int i = 0; i < m; ++i)
-            for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x) b[t.off_var + (x - p->row_ptr[i]) * m + i] = (uint16_t)p->col_idx[x];
+            for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x) b[t.off_var + (x - p->row_ptr[i]) * m + i] = (uint16_t)(4 * p->col_idx[x]);
         t.off_col_ptr = put(n + 1);
         for (int j = 0; j <= n; ++j) b[t.off_col_ptr + j] = (uint16_t)p->col_ptr[j];
         t.off_col_pos = put(E);
@@ -242,6 +265,29 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
         for (int x = 0; x < E; ++x) {
             b[t.off_col_pos + x] = (uint16_t)(col_slot[x] * m + p->row_idx[x]);
             b[t.off_col_chk + x] = (uint16_t)p->row_idx[x];
+        }
+        // min-sum variable-phase table: per variable dvs byte offsets into c2v, padded with the zero slot
+        t.dvs = is_ms ? (dv_inst <= 4 ? 4 : (dv_inst <= 8 ? 8 : 16)) : 0;
+        b.resize((b.size() + 7) & ~size_t(7), 0);              // 16-byte aligned rows
+        t.off_vn = put((n + 1) * t.dvs);
+        t.n_pad = (n + 31) & ~31;
+        if (is_ms)
+            for (int j = 0; j < n; ++j)
+                for (int x = 0; x < t.dvs; ++x) {
+                    const int e = p->col_ptr[j] + x;
+                    b[t.off_vn + j * t.dvs + x] = (uint16_t)(e < p->col_ptr[j + 1] ? 4 * (col_slot[e] * m + p->row_idx[e]) : 4 * dc * m);
+                }
+        if (is_ms) for (int x = 0; x < t.dvs; ++x) b[t.off_vn + n * t.dvs + x] = (uint16_t)(4 * dc * m);   // dummy variable n
+        t.off_rowpar = put(2 * t.mw);
+        for (int i = 0; i < m; ++i)
+            if ((p->row_ptr[i + 1] - p->row_ptr[i]) & 1) b[t.off_rowpar + 2 * (i >> 5) + ((i & 31) >> 4)] |= (uint16_t)(1u << (i & 15));
+        // lanes per check of each layer: the largest power of two (<= 8, <= row weight) that keeps the layer in one warp pass
+        t.off_layer_lpc = put(nl);
+        for (int l = 0; l < nl; ++l) {
+            const int lc = std::max(1, p->layer_ptr[l + 1] - p->layer_ptr[l]);
+            int lpc = 1;
+            while (lpc < 8 && lpc * 2 * lc <= 32 && lpc * 2 <= std::max(1, dc)) lpc *= 2;
+            b[t.off_layer_lpc + l] = (uint16_t)lpc;
         }
         t.off_layer_ptr = put(nl + 1);
         for (int l = 0; l <= nl; ++l) b[t.off_layer_ptr + l] = (uint16_t)p->layer_ptr[l];
@@ -260,6 +306,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             }
             std::sort(vs.begin(), vs.end());
             for (int v : vs) { seen[v] = 0; lvar.push_back((uint16_t)v); }
+            if (o->dec_type == QLDPC_MS) while (lvar.size() % 32) lvar.push_back((uint16_t)n);   // uniform trip count per lane
             lvar_ptr[l + 1] = (int)lvar.size();
         }
         if (lvar.size() > 65535) return bail(QLDPC_ETOOBIG, "per-layer variable lists exceed 65535 entries");
@@ -274,10 +321,8 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
         const size_t blob_bytes = ((size_t)t.len * 2 + 15) & ~size_t(15);
         size_t state = 0;
         const void *fn = nullptr;
-        if (o->dec_type == QLDPC_MS) {
+        if (is_ms) {
             state = ms_layout(t).bytes;
-            int dci = 0;
-            pk->ms = ms_select(dc, regular, &dci);
             fn = (const void *)pk->ms;
         } else {
             state = bp_layout(t).bytes;
@@ -339,7 +384,7 @@ int64_t qldpc_plan_info(const qldpc_plan *p, int what)
     case 5: return p->threads;
     case 6: return (int64_t)p->smem_bytes;
     case 7: return p->shots_per_cta;
-    case 8: return p->tab.dc;
+    case 8: return p->row_w;
     case 9: return p->tab.dv;
     case 10: return p->rank_h;
     }
@@ -362,6 +407,12 @@ static int launch_decode(qldpc_plan *p, const uint32_t *syn, int64_t shots, uint
     case QLDPC_MS: {
         MsConst c;
         c.L = o.prior_llr; c.Lf = (double)(float)o.prior_llr; c.beta = o.beta; c.max_iter = o.max_iter;
+        {   // smallest binary32 >= -L
+            const double T = -o.prior_llr;
+            float f = (float)T;
+            if ((double)f < T) f = std::nextafterf(f, INFINITY);
+            c.Tf = f;
+        }
         kernels_of(p)->ms<<<grid, p->threads, p->smem_bytes, st>>>(p->tab, p->d_blob, c, io);
         break;
     }
