@@ -22,7 +22,11 @@
 //     needs one binary32 compare and no stored decision bits: the previous decision is S_j(old) < Tf;
 //   * convergence is tested after every layer step (decoders.py:175-176) on an incrementally maintained count
 //     of unsatisfied checks: a flipped decision toggles the parity bits of its checks (shared-memory atomics,
-//     rare) and adds +-1 per toggled bit.
+//     rare) and adds +-1 per toggled bit;
+//   * control flow is kept warp-uniform everywhere (padded lists, selects instead of branches, cooperative flip
+//     handling): a lane-divergent loop was measured to split warps into halves that never reconverged.
+// Shared memory is addressed with explicit 32-bit shared-window addresses (ld.shared / st.shared) so that the
+// hot loops carry one integer add per access and no generic-pointer arithmetic.
 // No fused multiply-add may be formed in this file (compile with -fmad=false); every operation that the spec
 // rounds individually uses an explicit _rn intrinsic anyway.
 #pragma once
@@ -30,10 +34,12 @@
 
 namespace qldpc {
 
+constexpr int kMsMaxWarps = 24;   // 768 threads per CTA -> up to 85 registers per thread
+
 struct MsSmemLayout {
     // per-shot state, offsets in bytes from the warp's base
     int off_c2v;   // float [dc*m + 4]  (entry dc*m is the always-zero slot)
-    int off_S;     // float [n + 1] (entry n: dummy variable)
+    int off_S;     // float [n + 1] (entry n: dummy variable of the padded lists)
     int off_par;   // uint32 [mw]
     int off_syn;   // uint32 [mw]
     int bytes;     // multiple of 16
@@ -52,10 +58,15 @@ __host__ __device__ inline MsSmemLayout ms_layout(const Tables &t)
     return l;
 }
 
-__device__ __forceinline__ float lds_f32(const unsigned char *base, uint32_t byte_off)
-{
-    return *reinterpret_cast<const float *>(base + byte_off);
-}
+// ---- explicit shared-window accessors (addresses are 32-bit shared addresses)
+__device__ __forceinline__ float sld_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t sld_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t sld_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sst_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sst_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint2 sld_v2(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 sld_v4(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t satom_xor(uint32_t a, uint32_t v) { uint32_t o; asm volatile("atom.shared.xor.b32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o; }
 
 struct CnPartial {
     double m1, m2;   // smallest / second smallest |v2c| over the lane's slots (inf if none)
@@ -64,9 +75,9 @@ struct CnPartial {
 };
 
 // Merge two partial scans of disjoint slot sets.  Symmetric and branch-free on purpose (a lane-parity branch here
-// splits the warp in two halves that then run the rest of the decode separately): the winner is the smaller first
-// minimum, ties go to the lower slot, which preserves np.argmin's "first minimum" (decoders.py:161); the new second
-// minimum is the smaller of the loser's first and the winner's second minimum.
+// splits the warp): the winner is the smaller first minimum, ties go to the lower slot, which preserves np.argmin's
+// "first minimum" (decoders.py:161); the new second minimum is the smaller of the loser's first and the winner's
+// second minimum.
 __device__ __forceinline__ void cn_merge(CnPartial &a, const CnPartial &b)
 {
     const bool lt = (b.m1 < a.m1) | ((b.m1 == a.m1) & (b.k1 < a.k1));
@@ -78,32 +89,40 @@ __device__ __forceinline__ void cn_merge(CnPartial &a, const CnPartial &b)
     a.par ^= b.par;
 }
 
+struct MsAddr {          // shared-window byte addresses, warp-uniform
+    uint32_t var_tab;    // uint16 [dc*m]   (CTA tables)
+    uint32_t layer_chk;  // uint16 [...]
+    uint32_t c2v, S, par, syn;   // per-warp state
+    uint32_t m2;         // 2*m : byte stride of one slot row in var_tab
+    uint32_t m4;         // 4*m : byte stride of one slot row in c2v
+};
+
 // Check-node phase of one layer with LPC lanes per check (decoders.py:156-169).
 template <int DC, bool REGULAR, int LPC>
-__device__ __forceinline__ void ms_check_phase(int qb, int qe, int lane, int m, const uint16_t *__restrict__ layer_chk,
-                                               const uint16_t *__restrict__ var_tab, unsigned char *c2v_b,
-                                               const unsigned char *S_b, const uint32_t *syn, double prior, double beta)
+__device__ __forceinline__ void ms_check_phase(int qb, int qe, int lane, const MsAddr &A, double prior, double beta)
 {
     constexpr int SPL = (DC + LPC - 1) / LPC;       // slots per lane
     constexpr int CPP = 32 / LPC;                   // checks per pass
+    constexpr bool EXACT = (LPC * SPL == DC);       // no lane owns a slot >= DC
     const int h = lane % LPC;                       // which slice of the row
+    const int k0 = h * SPL;                         // first slot of the lane
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
     for (int q0 = qb; q0 < qe; q0 += CPP) {
         const int q = q0 + lane / LPC;
         const bool act = q < qe;
-        const int i = layer_chk[act ? q : qb];
+        const uint32_t i = sld_u16(A.layer_chk + 2u * (uint32_t)(act ? q : qb));
+        const uint32_t vt = A.var_tab + (uint32_t)k0 * A.m2 + 2u * i;    // &var_tab[k0*m + i]
+        const uint32_t cv = A.c2v + (uint32_t)k0 * A.m4 + 4u * i;        // &c2v[k0*m + i]
         CnPartial pr;
         pr.m1 = inf; pr.m2 = inf; pr.k1 = 0; pr.par = 0u;
         uint32_t sb = 0;                            // sign bits of the lane's own slots
 #pragma unroll
         for (int s = 0; s < SPL; ++s) {
-            const int k = h * SPL + s;
-            if (k < DC) {
-                const int pos = k * m + i;
-                const uint32_t joff = var_tab[pos];                         // byte offset of S_j, kPad past a short row
+            if (EXACT || k0 + s < DC) {
+                const uint32_t joff = sld_u16(vt + (uint32_t)s * A.m2);       // byte offset of S_j, kPad past a short row
                 if (REGULAR || joff != kPad) {
-                    const double post = __dadd_rn(prior, (double)lds_f32(S_b, joff));          // :173
-                    const double v = __dsub_rn(post, (double)lds_f32(c2v_b, 4u * pos));      // :177
+                    const double post = __dadd_rn(prior, (double)sld_f32(A.S + joff));                   // :173
+                    const double v = __dsub_rn(post, (double)sld_f32(cv + (uint32_t)s * A.m4));          // :177
                     const double av = fabs(v);
                     const uint32_t neg = v < 0.0 ? 1u : 0u;                                   // :157-158 (0 -> +1)
                     sb |= neg << s;
@@ -111,7 +130,7 @@ __device__ __forceinline__ void ms_check_phase(int qb, int qe, int lane, int m, 
                     const bool lt1 = av < pr.m1, lt2 = av < pr.m2;                            // selects, not branches
                     pr.m2 = lt1 ? pr.m1 : (lt2 ? av : pr.m2);                                 // min over the others (:162-164)
                     pr.m1 = lt1 ? av : pr.m1;                                                 // first argmin (:161)
-                    pr.k1 = lt1 ? k : pr.k1;
+                    pr.k1 = lt1 ? (k0 + s) : pr.k1;
                 }
             }
         }
@@ -127,22 +146,24 @@ __device__ __forceinline__ void ms_check_phase(int qb, int qe, int lane, int m, 
             cn_merge(pr, o);
         }
         if (act) {
-            double m1 = pr.m1, m2 = pr.m2;
-            if (isinf(m1)) m1 = 0.0;                                                          // :165
-            if (isinf(m2)) m2 = 0.0;                                                          // :166
-            float r1 = __double2float_rn(__dmul_rn(beta, m1));                                // f64 product, f32 store (:167)
-            float r2 = __double2float_rn(__dmul_rn(beta, m2));                                // (:168)
-            if (isinf(r1)) r1 = 0.0f;                                                         // :169
-            if (isinf(r2)) r2 = 0.0f;
-            const uint32_t P = pr.par ^ ((syn[i >> 5] >> (i & 31)) & 1u);                     // sign product x syndrome sign (:151,:159)
+            // inf -> 0 for an empty / single-edge row (:165-166); f64 product, f32 store (:167-168); an overflowed
+            // binary32 message is zeroed (:169)
+            const double m1 = (pr.m1 == inf) ? 0.0 : pr.m1;
+            const double m2 = (pr.m2 == inf) ? 0.0 : pr.m2;
+            float r1 = __double2float_rn(__dmul_rn(beta, m1));
+            float r2 = __double2float_rn(__dmul_rn(beta, m2));
+            r1 = (fabsf(r1) == __int_as_float(0x7f800000)) ? 0.0f : r1;
+            r2 = (fabsf(r2) == __int_as_float(0x7f800000)) ? 0.0f : r2;
+            const uint32_t synbit = (sld_u32(A.syn + 4u * (i >> 5)) >> (i & 31u)) & 1u;
+            const uint32_t P = pr.par ^ synbit;                                               // sign product x syndrome sign (:151,:159)
+            const int kk = pr.k1 - k0;                                                        // local slot of the minimum (if mine)
 #pragma unroll
             for (int s = 0; s < SPL; ++s) {
-                const int k = h * SPL + s;
-                if (k < DC) {
-                    const int pos = k * m + i;
-                    if (REGULAR || var_tab[pos] != kPad) {
-                        const float mag = (k == pr.k1) ? r2 : r1;
-                        *reinterpret_cast<float *>(c2v_b + 4u * pos) = (((sb >> s) & 1u) ^ P) ? -mag : mag;
+                if (EXACT || k0 + s < DC) {
+                    if (REGULAR || sld_u16(vt + (uint32_t)s * A.m2) != kPad) {
+                        const float mag = (s == kk) ? r2 : r1;
+                        const uint32_t bits = __float_as_uint(mag) ^ ((((sb >> s) & 1u) ^ P) << 31);
+                        sst_f32(cv + (uint32_t)s * A.m4, __uint_as_float(bits));
                     }
                 }
             }
@@ -157,65 +178,96 @@ struct VnRow {
     static constexpr int DVS = DV <= 4 ? 4 : (DV <= 8 ? 8 : 16);
 };
 
+// S_j = sequential binary32 sum of the c2v of variable j in ascending check order (decoders.py:172).  The first term
+// is taken as is (0.0f + c only differs from c for c == -0.0f, and the sign of a zero sum is never observable).
 template <int DV>
-__device__ __forceinline__ float ms_colsum(const unsigned char *c2v_b, const uint16_t *vrow)
+__device__ __forceinline__ float ms_colsum(uint32_t c2v, uint32_t vrow)
 {
     constexpr int DVS = VnRow<DV>::DVS;
     uint32_t w[DVS / 2];
     if (DVS == 4) {
-        const uint2 a = *reinterpret_cast<const uint2 *>(vrow);
+        const uint2 a = sld_v2(vrow);
         w[0] = a.x; w[1] = a.y;
     } else {
 #pragma unroll
         for (int x = 0; x < DVS / 8; ++x) {
-            const uint4 a = *reinterpret_cast<const uint4 *>(vrow + 8 * x);
+            const uint4 a = sld_v4(vrow + 16u * x);
             w[4 * x + 0] = a.x; w[4 * x + 1] = a.y; w[4 * x + 2] = a.z; w[4 * x + 3] = a.w;
         }
     }
-    float s = 0.0f;
+    float term[DV];
 #pragma unroll
     for (int x = 0; x < DV; ++x) {
         const uint32_t off = (x & 1) ? (w[x >> 1] >> 16) : (w[x >> 1] & 0xffffu);
-        s = __fadd_rn(s, lds_f32(c2v_b, off));                       // sequential f32, ascending check (:172)
+        term[x] = sld_f32(c2v + off);
     }
+    float s = term[0];
+#pragma unroll
+    for (int x = 1; x < DV; ++x) s = __fadd_rn(s, term[x]);
     return s;
 }
 
+// One variable-node pass over variable j of every lane: new sum, store, flip detection and cooperative parity update.
+template <int DV>
+__device__ __forceinline__ void ms_var_update(uint32_t j, int lane, const MsAddr &A, uint32_t vn_tab, uint32_t col_ptr,
+                                              uint32_t col_chk, float Tf, int &delta)
+{
+    constexpr int DVS = VnRow<DV>::DVS;
+    const uint32_t sa = A.S + 4u * j;
+    const float s_old = sld_f32(sa);
+    const float s = ms_colsum<DV>(A.c2v, vn_tab + (uint32_t)(2 * DVS) * j);
+    sst_f32(sa, s);
+    uint32_t flips = __ballot_sync(0xffffffffu, (s < Tf) != (s_old < Tf));     // hard decision flipped (:173-174)
+    while (flips) {                                                              // rare; one flipped variable per trip
+        const int src = __ffs(flips) - 1;
+        flips &= flips - 1;
+        const uint32_t jf = __shfl_sync(0xffffffffu, j, src);
+        const uint32_t x0 = sld_u16(col_ptr + 2u * jf), x1 = sld_u16(col_ptr + 2u * jf + 2u);
+        const uint32_t x = x0 + lane;
+        if (x < x1) {                                                            // lane <-> check of the flipped variable
+            const uint32_t ch = sld_u16(col_chk + 2u * x);
+            const uint32_t bit = 1u << (ch & 31u);
+            const uint32_t old = satom_xor(A.par + 4u * (ch >> 5), bit);
+            delta += (old & bit) ? -1 : 1;
+        }
+    }
+}
+
 template <int DC, bool REGULAR, int DV>
-__global__ void __launch_bounds__(1024, 1) ms_decode_kernel(Tables t, const uint16_t *__restrict__ blob, MsConst c, DecodeIO io)
+__global__ void __launch_bounds__(kMsMaxWarps * 32, 1) ms_decode_kernel(Tables t, const uint16_t *__restrict__ blob, MsConst c, DecodeIO io)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    uint16_t *tab = reinterpret_cast<uint16_t *>(smem);
     {   // graph tables -> shared memory (once per CTA), 16 B per thread per trip
         const uint4 *src = reinterpret_cast<const uint4 *>(blob);
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
         for (int i = threadIdx.x; i < t.len / 8; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    const uint16_t *var_tab = tab + t.off_var;          // byte offsets into S
-    const uint16_t *col_ptr = tab + t.off_col_ptr;
-    const uint16_t *col_chk = tab + t.off_col_chk;
-    const uint16_t *layer_ptr = tab + t.off_layer_ptr;
-    const uint16_t *layer_chk = tab + t.off_layer_chk;
-    const uint16_t *layer_lpc = tab + t.off_layer_lpc;
-    const uint16_t *lvar_ptr = tab + t.off_lvar_ptr;
-    const uint16_t *lvar_idx = tab + t.off_lvar_idx;
-    const uint16_t *vn_tab = tab + t.off_vn;            // [n][DVS] byte offsets into c2v
-    constexpr int DVS = VnRow<DV>::DVS;
-
-    const MsSmemLayout lay = ms_layout(t);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char *base = smem + ((t.len * 2 + 15) & ~15) + (size_t)warp * lay.bytes;
-    unsigned char *c2v_b = base + lay.off_c2v;
-    unsigned char *S_b = base + lay.off_S;
-    float *c2v = reinterpret_cast<float *>(c2v_b);
-    float *S = reinterpret_cast<float *>(S_b);   // [n + 1]: entry n is the dummy variable of the padded lists
-    uint32_t *par = reinterpret_cast<uint32_t *>(base + lay.off_par);
-    uint32_t *syn = reinterpret_cast<uint32_t *>(base + lay.off_syn);
-    const int m = t.m, n = t.n;
     const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(full, (int)(threadIdx.x >> 5), 0);      // provably warp-uniform
+    const MsSmemLayout lay = ms_layout(t);
+    uint32_t tab;                                                         // shared-window address of the CTA tables
+    // opaque to the optimiser on purpose: a plain __cvta_generic_to_shared gets rematerialised (S2UR + ULEA) in every loop
+    asm volatile("{ .reg .u64 t64; cvta.to.shared.u64 t64, %1; cvt.u32.u64 %0, t64; }" : "=r"(tab) : "l"(smem));
+    const uint32_t wbase = tab + (uint32_t)((t.len * 2 + 15) & ~15) + (uint32_t)warp * (uint32_t)lay.bytes;
+    MsAddr A;
+    A.var_tab = tab + 2u * t.off_var;
+    A.layer_chk = tab + 2u * t.off_layer_chk;
+    A.c2v = wbase + lay.off_c2v;
+    A.S = wbase + lay.off_S;
+    A.par = wbase + lay.off_par;
+    A.syn = wbase + lay.off_syn;
+    A.m2 = 2u * t.m;
+    A.m4 = 4u * t.m;
+    const uint32_t col_ptr = tab + 2u * t.off_col_ptr, col_chk = tab + 2u * t.off_col_chk;
+    const uint32_t layer_ptr = tab + 2u * t.off_layer_ptr, layer_lpc = tab + 2u * t.off_layer_lpc;
+    const uint32_t lvar_ptr = tab + 2u * t.off_lvar_ptr, lvar_idx = tab + 2u * t.off_lvar_idx;
+    const uint32_t vn_tab = tab + 2u * t.off_vn, rowpar = tab + 2u * t.off_rowpar;
+    const int n = t.n;
     const float Tf = c.Tf;
     const bool init_bit = 0.0f < Tf;                    // decision of a variable whose sum is still 0 (only if L < 0)
+    const int c2v_words = t.dc * t.m + 4;
 
     for (;;) {
         long long shot = 0;
@@ -224,78 +276,65 @@ __global__ void __launch_bounds__(1024, 1) ms_decode_kernel(Tables t, const uint
         if (shot >= io.shots) break;
 
         // ---- initial state: c2v = 0 (decoders.py:150), S = 0, residual = syndrome (+ H.1 if the all-zero sums decide 1)
-        {
-            float4 *z = reinterpret_cast<float4 *>(c2v);
-            const int n4 = (t.dc * m + 4) / 4;
-            for (int i = lane; i < n4; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int i = n4 * 4 + lane; i < t.dc * m + 4; i += 32) c2v[i] = 0.0f;
-        }
-        for (int i = lane; i <= n; i += 32) S[i] = 0.0f;
+        for (int i = lane * 4; i < c2v_words; i += 128)
+            asm volatile("st.shared.v4.f32 [%0], {%1,%1,%1,%1};" :: "r"(A.c2v + 4u * i), "f"(0.0f) : "memory");
+        for (int i = lane; i <= n; i += 32) sst_f32(A.S + 4u * i, 0.0f);
         int unsat = 0;
         for (int i = lane; i < t.mw; i += 32) {
             const uint32_t w = io.syn[shot * t.mw + i];
-            const uint32_t p0 = init_bit ? (w ^ (tab + t.off_rowpar)[2 * i] ^ ((uint32_t)(tab + t.off_rowpar)[2 * i + 1] << 16)) : w;
-            syn[i] = w;
-            par[i] = p0;
+            const uint32_t p0 = init_bit ? (w ^ sld_u32(rowpar + 4u * i)) : w;
+            sst_u32(A.syn + 4u * i, w);
+            sst_u32(A.par + 4u * i, p0);
             unsat += __popc(p0);
         }
         unsat = __reduce_add_sync(full, unsat);
         __syncwarp();
 
         bool converged = false;
-        bool first = true;
         int it = 0;
+        if (c.max_iter > 0) {
+            // ---------------- first layer step: prior is the binary32-rounded L (decoders.py:148-149) and the variable
+            // phase visits EVERY variable (the reference recomputes all posteriors; a variable outside layer 0 has
+            // posterior L, which may be negative for p > 1/2)
+            const int qb = sld_u16(layer_ptr), qe = sld_u16(layer_ptr + 2u);
+            ms_check_phase<DC, REGULAR, 1>(qb, qe, lane, A, c.Lf, c.beta);
+            __syncwarp();
+            int delta = 0;
+            for (int q = lane; q < t.n_pad; q += 32)
+                ms_var_update<DV>((uint32_t)(q < n ? q : n), lane, A, vn_tab, col_ptr, col_chk, Tf, delta);
+            unsat += __reduce_add_sync(full, delta);
+            __syncwarp();
+            converged = unsat == 0;
+        }
         for (; it < c.max_iter && !converged; ++it) {
-            for (int l = 0; l < t.nl; ++l) {
-                const double prior = first ? c.Lf : c.L;
+            for (int l = (it == 0 ? 1 : 0); l < t.nl; ++l) {
                 // ---------------- check-node phase (decoders.py:156-169)
-                const int qb = layer_ptr[l], qe = layer_ptr[l + 1];
-                const int lpc = layer_lpc[l];
-                if (lpc == 1) ms_check_phase<DC, REGULAR, 1>(qb, qe, lane, m, layer_chk, var_tab, c2v_b, S_b, syn, prior, c.beta);
-                else if (lpc == 2) ms_check_phase<DC, REGULAR, 2>(qb, qe, lane, m, layer_chk, var_tab, c2v_b, S_b, syn, prior, c.beta);
-                else if (lpc == 4) ms_check_phase<DC, REGULAR, 4>(qb, qe, lane, m, layer_chk, var_tab, c2v_b, S_b, syn, prior, c.beta);
-                else ms_check_phase<DC, REGULAR, 8>(qb, qe, lane, m, layer_chk, var_tab, c2v_b, S_b, syn, prior, c.beta);
+                const int qb = sld_u16(layer_ptr + 2u * l), qe = sld_u16(layer_ptr + 2u * l + 2u);
+                const int lpc = sld_u16(layer_lpc + 2u * l);
+                if (lpc == 1) ms_check_phase<DC, REGULAR, 1>(qb, qe, lane, A, c.L, c.beta);
+                else if (lpc == 2) ms_check_phase<DC, REGULAR, 2>(qb, qe, lane, A, c.L, c.beta);
+                else if (lpc == 4) ms_check_phase<DC, REGULAR, 4>(qb, qe, lane, A, c.L, c.beta);
+                else ms_check_phase<DC, REGULAR, 8>(qb, qe, lane, A, c.L, c.beta);
                 __syncwarp();
-                // ---------------- variable-node phase (decoders.py:172-174) on the variables whose sums changed;
-                // the very first step visits every variable (the reference recomputes all posteriors, and a
-                // variable outside layer 0 has posterior L, which may be negative for p > 1/2).
-                // Control flow below is warp-uniform on purpose: every lane runs the same number of trips (the lists are
-                // padded to a multiple of 32 with the dummy variable n, whose table row points at the zero slot) and
-                // flips are handled cooperatively after a ballot.  A lane-divergent loop here was measured to split
-                // the warp into two halves that never reconverged (BSSY/BSYNC membership is per split group).
-                const int vb = first ? 0 : lvar_ptr[l], ve = first ? t.n_pad : lvar_ptr[l + 1];
+                // ---------------- variable-node phase (decoders.py:172-174) on the variables whose sums changed.  Every
+                // lane runs the same number of trips (lists are padded to a multiple of 32 with the dummy variable n).
+                const int vb = sld_u16(lvar_ptr + 2u * l), ve = sld_u16(lvar_ptr + 2u * l + 2u);
                 int delta = 0;
-                for (int q = vb + lane; q < ve; q += 32) {
-                    const int j = first ? (q < n ? q : n) : lvar_idx[q];
-                    const float s = ms_colsum<DV>(c2v_b, vn_tab + j * DVS);
-                    const float s_old = S[j];
-                    S[j] = s;
-                    uint32_t flips = __ballot_sync(full, (s < Tf) != (s_old < Tf));     // hard decision flipped (:173-174)
-                    while (flips) {                                                      // rare; one flipped variable per trip
-                        const int src = __ffs(flips) - 1;
-                        flips &= flips - 1;
-                        const int jf = __shfl_sync(full, j, src);
-                        const int x = col_ptr[jf] + lane;
-                        if (x < col_ptr[jf + 1]) {                                       // lane <-> check of the flipped variable
-                            const int ch = col_chk[x];
-                            const uint32_t bit = 1u << (ch & 31);
-                            const uint32_t old = atomicXor(&par[ch >> 5], bit);
-                            delta += (old & bit) ? -1 : 1;
-                        }
-                    }
-                }
+                for (int q = vb + lane; q < ve; q += 32)
+                    ms_var_update<DV>(sld_u16(lvar_idx + 2u * q), lane, A, vn_tab, col_ptr, col_chk, Tf, delta);
                 unsat += __reduce_add_sync(full, delta);
                 __syncwarp();
-                first = false;
                 // ---------------- H e == syndrome ?  (decoders.py:175-176)
                 if (unsat == 0) { converged = true; break; }
             }
         }
-        const int iters = it;   // the outer ++it has already run after a converging break: it+1 of decoders.py:176, else max_iter (:182)
+        // iterations: it+1 of decoders.py:176 on a converging break (the outer ++it has already run; a convergence in the
+        // very first step leaves it == 0), else max_iter (:182)
+        const int iters = (converged && it == 0) ? 1 : it;
         // ---- outputs: e_j = (S_j < Tf)
         for (int w = 0; w < t.nw; ++w) {
             const int j = w * 32 + lane;
-            const uint32_t bits = __ballot_sync(full, j < n && (c.max_iter > 0 ? S[j] < Tf : false));
+            const uint32_t bits = __ballot_sync(full, j < n && c.max_iter > 0 && sld_f32(A.S + 4u * (uint32_t)(j < n ? j : n)) < Tf);
             if (lane == 0) io.ehat[shot * t.nw + w] = bits;
         }
         if (lane == 0) {
@@ -304,7 +343,7 @@ __global__ void __launch_bounds__(1024, 1) ms_decode_kernel(Tables t, const uint
         }
         if (io.llr) {
             double *dst = io.llr + shot * (long long)n;
-            for (int j = lane; j < n; j += 32) dst[j] = __dadd_rn(c.L, (double)S[j]);
+            for (int j = lane; j < n; j += 32) dst[j] = __dadd_rn(c.L, (double)sld_f32(A.S + 4u * j));
         }
         if (!converged && io.fail_count) {
             int slot = 0;
@@ -313,7 +352,7 @@ __global__ void __launch_bounds__(1024, 1) ms_decode_kernel(Tables t, const uint
             if (slot < io.fail_cap) {
                 if (lane == 0) io.fail_shot[slot] = (int)shot;
                 double *dst = io.fail_llr + (long long)slot * n;
-                for (int j = lane; j < n; j += 32) dst[j] = __dadd_rn(c.L, (double)S[j]);
+                for (int j = lane; j < n; j += 32) dst[j] = __dadd_rn(c.L, (double)sld_f32(A.S + 4u * j));
             }
         }
         __syncwarp();

@@ -332,7 +332,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
         if (!fn) return bail(QLDPC_ETOOBIG, "row weight not supported");
         if (blob_bytes + state > (size_t)kMaxSmemPerCta)
             return bail(QLDPC_ETOOBIG, "decoder state of one shot does not fit in 227 KB of shared memory");
-        int warps = (int)std::min<size_t>(32, ((size_t)kMaxSmemPerCta - blob_bytes) / state);
+        int warps = (int)std::min<size_t>(is_ms ? kMsMaxWarps : 32, ((size_t)kMaxSmemPerCta - blob_bytes) / state);
         p->state_bytes = state;
         p->threads = warps * kWarp;
         p->shots_per_cta = warps;
