@@ -2,9 +2,16 @@
 //
 // Semantics: decoders.py:189-290 (CPU restatement oracle/qldpc_oracle.c:bp_decode_one).
 // Same execution shape as the min-sum kernel (one warp per shot, persistent CTAs, state in shared memory,
-// slot-major edges).  v2c is rebuilt as T_j - c2v_e with T_j = L0 + sum_j (decoders.py:269), which is the value
-// the reference stored after the previous layer step.  The column sum follows NumPy's np.sum order on the
-// gathered vector: sequential below 8 terms, the 8-accumulator pairwise pattern from 8 terms on.
+// slot-major edges, warp-uniform control flow).  v2c is rebuilt as T_j - c2v_e with T_j = L0 + sum_j
+// (decoders.py:269), which is the value the reference stored after the previous layer step.
+//   * check phase: lane <-> EDGE (LPC = 4, 8, 16 or 32 lanes per check).  tanh, the division and atanh -- the
+//     expensive part -- run on all lanes in parallel; the product prod = ((t0 t1) t2) ... is formed in the
+//     reference's order (np.prod is sequential, ascending variable, decoders.py:253-254) by a uniform loop of
+//     shuffles, every lane of the check computing the same value (padding lanes contribute the factor 1.0).
+//   * variable phase: lane <-> variable; the column sum follows NumPy's np.sum order on the gathered vector:
+//     sequential below 8 terms, the 8-accumulator pairwise pattern from 8 terms on (oracle: numpy_sum_f64).
+//   * hard decision T_j < 0, previous decision = sign of the old T_j; flips update the residual parity words
+//     cooperatively and maintain the count of unsatisfied checks (decoders.py:280-285).
 #pragma once
 #include "common.cuh"
 
@@ -18,8 +25,8 @@ struct BpConst {
 
 struct BpSmemLayout {
     int off_c2v;   // double [dc*m]
-    int off_T;     // double [n]
-    int off_e, off_par, off_syn;
+    int off_T;     // double [n + 1]
+    int off_par, off_syn;
     int bytes;
 };
 
@@ -28,21 +35,27 @@ __host__ __device__ inline BpSmemLayout bp_layout(const Tables &t)
     BpSmemLayout l;
     int o = 0;
     l.off_c2v = o; o += 8 * t.dc * t.m;
-    l.off_T = o;   o += 8 * t.n;
-    l.off_e = o;   o += 4 * t.nw;
+    l.off_T = o;   o += 8 * (t.n + 1);
     l.off_par = o; o += 4 * t.mw;
     l.off_syn = o; o += 4 * t.mw;
     l.bytes = (o + 15) & ~15;
     return l;
 }
 
-// np.sum(c2v[edges of j]) -- see numpy_sum_f64 in the oracle.
-__device__ __forceinline__ double bp_colsum(const double *c2v, const uint16_t *col_pos, int t0, int t1)
+// np.sum(c2v[edges of j]) with a warp-uniform trip count (dv_max); terms past the degree are skipped by predicate.
+__device__ __forceinline__ double bp_colsum(const double *c2v, const uint16_t *col_pos, int t0, int cnt, int dv_max)
 {
-    const int cnt = t1 - t0;
-    if (cnt < 8) {
+    if (dv_max < 8) {
         double s = 0.0;
-        for (int x = t0; x < t1; ++x) s = __dadd_rn(s, c2v[col_pos[x]]);
+        for (int x = 0; x < dv_max; ++x) {
+            const double term = c2v[col_pos[t0 + (x < cnt ? x : 0)]];
+            s = (x < cnt) ? __dadd_rn(s, term) : s;
+        }
+        return s;
+    }
+    if (cnt < 8) {                                   // mixed degrees around 8: rare, lane-divergent but correct
+        double s = 0.0;
+        for (int x = 0; x < cnt; ++x) s = __dadd_rn(s, c2v[col_pos[t0 + x]]);
         return s;
     }
     double r[8];
@@ -59,6 +72,7 @@ __device__ __forceinline__ double bp_colsum(const double *c2v, const uint16_t *c
     return res;
 }
 
+template <int LPC>
 __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint16_t *__restrict__ blob, BpConst c, DecodeIO io)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -69,7 +83,7 @@ __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint
         for (int i = threadIdx.x; i < t.len / 8; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    const uint16_t *var_tab = tab + t.off_var;
+    const uint16_t *var_tab = tab + t.off_var;          // byte offsets 4*j
     const uint16_t *col_ptr = tab + t.off_col_ptr;
     const uint16_t *col_pos = tab + t.off_col_pos;
     const uint16_t *col_chk = tab + t.off_col_chk;
@@ -77,18 +91,23 @@ __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint
     const uint16_t *layer_chk = tab + t.off_layer_chk;
     const uint16_t *lvar_ptr = tab + t.off_lvar_ptr;
     const uint16_t *lvar_idx = tab + t.off_lvar_idx;
+    const uint32_t *rowpar = reinterpret_cast<const uint32_t *>(tab + t.off_rowpar);
 
     const BpSmemLayout lay = bp_layout(t);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(full, (int)(threadIdx.x >> 5), 0);
     unsigned char *base = smem + ((t.len * 2 + 15) & ~15) + (size_t)warp * lay.bytes;
     double *c2v = reinterpret_cast<double *>(base + lay.off_c2v);
     double *T = reinterpret_cast<double *>(base + lay.off_T);
-    uint32_t *eb = reinterpret_cast<uint32_t *>(base + lay.off_e);
     uint32_t *par = reinterpret_cast<uint32_t *>(base + lay.off_par);
     uint32_t *syn = reinterpret_cast<uint32_t *>(base + lay.off_syn);
     const int m = t.m, n = t.n, dc = t.dc;
-    const unsigned full = 0xffffffffu;
     const double one_m_eps = 1.0 - c.eps;                     // `1-eps` of decoders.py:257
+    const bool init_bit = c.L0 < 0.0;
+    constexpr int CPP = 32 / LPC;
+    const int k = lane % LPC;                                  // slot of this lane
+    const int grp = lane & ~(LPC - 1);                         // first lane of the check's group
 
     for (;;) {
         long long shot = 0;
@@ -96,72 +115,83 @@ __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint
         shot = __shfl_sync(full, shot, 0);
         if (shot >= io.shots) break;
         for (int i = lane; i < dc * m; i += 32) c2v[i] = 0.0;       // :236
-        for (int i = lane; i < n; i += 32) T[i] = c.L0;             // v2c = L0 (:235)
-        for (int i = lane; i < t.nw; i += 32) eb[i] = 0u;
-        for (int i = lane; i < t.mw; i += 32) { uint32_t w = io.syn[shot * t.mw + i]; syn[i] = w; par[i] = w; }
+        for (int i = lane; i <= n; i += 32) T[i] = c.L0;            // v2c = L0 (:235)
+        int unsat = 0;
+        for (int i = lane; i < t.mw; i += 32) {
+            const uint32_t w = io.syn[shot * t.mw + i];
+            const uint32_t p0 = init_bit ? (w ^ rowpar[i]) : w;
+            syn[i] = w; par[i] = p0;
+            unsat += __popc(p0);
+        }
+        unsat = __reduce_add_sync(full, unsat);
         __syncwarp();
 
         bool converged = false, first = true;
         int it = 0;
         for (; it < c.max_iter && !converged; ++it) {
             for (int l = 0; l < t.nl; ++l) {
-                // ---------------- check-node phase (decoders.py:249-262)
+                // ---------------- check-node phase (decoders.py:249-262), one lane per edge
                 const int qb = layer_ptr[l], qe = layer_ptr[l + 1];
-                for (int q = qb + lane; q < qe; q += 32) {
-                    const int i = layer_chk[q];
+                for (int q0 = qb; q0 < qe; q0 += CPP) {
+                    const int q = q0 + lane / LPC;
+                    const bool act = q < qe;
+                    const int i = layer_chk[act ? q : qb];
+                    const int pos = (k < dc ? k : 0) * m + i;
+                    const uint32_t joff = var_tab[pos];
+                    const bool valid = act && k < dc && joff != kPad;
+                    double tk = 1.0;
+                    if (valid) tk = tanh(__dsub_rn(T[joff >> 2], c2v[pos]) / 2.0);     // tanh(v2c/2) (:254, :256)
                     double prod = 1.0;
-                    int deg = 0;
-                    for (int k = 0; k < dc; ++k) {
-                        const int pos = k * m + i;
-                        const uint32_t joff = var_tab[pos];                      // byte offset 4*j
-                        if (joff == kPad) break;
-                        const double v = __dsub_rn(T[joff >> 2], c2v[pos]);
-                        prod = __dmul_rn(prod, tanh(v / 2.0));                     // :253-254 (np.prod is sequential)
-                        ++deg;
-                    }
-                    const bool neg = (syn[i >> 5] >> (i & 31)) & 1u;
-                    // second pass: the v2c values are still intact (c2v of this row is only overwritten below,
-                    // position by position, after its own v2c has been rebuilt)
-                    for (int k = 0; k < deg; ++k) {
-                        const int pos = k * m + i;
-                        const double v = __dsub_rn(T[var_tab[pos] >> 2], c2v[pos]);
-                        double th2 = prod / tanh(v / 2.0);                         // :256
-                        if (fabs(th2) >= one_m_eps) {                              // :257-258
+                    for (int x = 0; x < dc; ++x)                                       // np.prod: sequential (:253-254)
+                        prod = __dmul_rn(prod, __shfl_sync(full, tk, grp + x));
+                    if (valid) {
+                        double th2 = prod / tk;                                        // :256
+                        if (fabs(th2) >= one_m_eps) {                                  // :257-258
                             const double sg = (th2 > 0.0) ? 1.0 : ((th2 < 0.0) ? -1.0 : 0.0);
                             th2 = __dsub_rn(th2, __dmul_rn(c.eps, sg));
                         }
-                        double val = 2.0 * atanh(th2);                             // :259
-                        if (neg) val = -val;                                       // :260-261
-                        c2v[pos] = val;                                            // :262
+                        double val = 2.0 * atanh(th2);                                 // :259
+                        if ((syn[i >> 5] >> (i & 31)) & 1u) val = -val;                // :260-261
+                        c2v[pos] = val;                                                // :262
                     }
+                    __syncwarp();
                 }
                 __syncwarp();
                 // ---------------- variable-node phase (decoders.py:265-280) on the variables whose messages changed
-                const int vb = first ? 0 : lvar_ptr[l], ve = first ? n : lvar_ptr[l + 1];
+                const int vb = first ? 0 : lvar_ptr[l], ve = first ? t.n_pad : lvar_ptr[l + 1];
+                int delta = 0;
                 for (int q = vb + lane; q < ve; q += 32) {
-                    const int j = first ? q : lvar_idx[q];
-                    const int t0 = col_ptr[j], t1 = col_ptr[j + 1];
-                    const double tot = __dadd_rn(c.L0, bp_colsum(c2v, col_pos, t0, t1));   // :269 / :275
+                    const int j = first ? (q < n ? q : n) : lvar_idx[q];
+                    const int t0 = (j < n) ? col_ptr[j] : 0, cnt = (j < n) ? col_ptr[j + 1] - t0 : 0;
+                    const double tot = __dadd_rn(c.L0, bp_colsum(c2v, col_pos, t0, cnt, t.dv));   // :269 / :275
+                    const double t_old = T[j];
                     T[j] = tot;
-                    const uint32_t bit = tot < 0.0 ? 1u : 0u;                      // :280
-                    const uint32_t old = (eb[j >> 5] >> (j & 31)) & 1u;
-                    if (bit != old) {
-                        atomicXor(&eb[j >> 5], 1u << (j & 31));
-                        for (int x = t0; x < t1; ++x) {
+                    uint32_t flips = __ballot_sync(full, (tot < 0.0) != (t_old < 0.0));           // :280
+                    while (flips) {
+                        const int src = __ffs(flips) - 1;
+                        flips &= flips - 1;
+                        const int jf = __shfl_sync(full, j, src);
+                        const int x = col_ptr[jf] + lane;
+                        if (x < col_ptr[jf + 1]) {
                             const int ch = col_chk[x];
-                            atomicXor(&par[ch >> 5], 1u << (ch & 31));
+                            const uint32_t bit = 1u << (ch & 31);
+                            const uint32_t old = atomicXor(&par[ch >> 5], bit);
+                            delta += (old & bit) ? -1 : 1;
                         }
                     }
                 }
+                unsat += __reduce_add_sync(full, delta);
                 __syncwarp();
                 first = false;
-                uint32_t nz = 0;
-                for (int w = lane; w < t.mw; w += 32) nz |= par[w];
-                if (!__any_sync(full, nz != 0)) { converged = true; break; }       // :283-285
+                if (unsat == 0) { converged = true; break; }                           // :283-285
             }
         }
-        const int iters = it;
-        for (int w = lane; w < t.nw; w += 32) io.ehat[shot * t.nw + w] = eb[w];
+        const int iters = it;   // ++it has run after a converging break: it+1 of :285, else max_iter
+        for (int w = 0; w < t.nw; ++w) {
+            const int j = w * 32 + lane;
+            const uint32_t bits = __ballot_sync(full, j < n && c.max_iter > 0 && T[j < n ? j : n] < 0.0);
+            if (lane == 0) io.ehat[shot * t.nw + w] = bits;
+        }
         if (lane == 0) { io.iters[shot] = iters; if (io.conv) io.conv[shot] = converged ? 1 : 0; }
         if (io.llr) {
             double *dst = io.llr + shot * (long long)n;

@@ -306,7 +306,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             }
             std::sort(vs.begin(), vs.end());
             for (int v : vs) { seen[v] = 0; lvar.push_back((uint16_t)v); }
-            if (o->dec_type == QLDPC_MS) while (lvar.size() % 32) lvar.push_back((uint16_t)n);   // uniform trip count per lane
+            while (lvar.size() % 32) lvar.push_back((uint16_t)n);   // dummy variable n: uniform trip count per lane
             lvar_ptr[l + 1] = (int)lvar.size();
         }
         if (lvar.size() > 65535) return bail(QLDPC_ETOOBIG, "per-layer variable lists exceed 65535 entries");
@@ -326,7 +326,11 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             fn = (const void *)pk->ms;
         } else {
             state = bp_layout(t).bytes;
-            pk->bp = bp_decode_kernel;
+            // lanes per check = smallest power of two >= row weight (one lane per edge)
+            if (dc <= 4) pk->bp = bp_decode_kernel<4>;
+            else if (dc <= 8) pk->bp = bp_decode_kernel<8>;
+            else if (dc <= 16) pk->bp = bp_decode_kernel<16>;
+            else pk->bp = bp_decode_kernel<32>;
             fn = (const void *)pk->bp;
         }
         if (!fn) return bail(QLDPC_ETOOBIG, "row weight not supported");

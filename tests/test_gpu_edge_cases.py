@@ -1,0 +1,170 @@
+"""Edge cases on the GPU against the CPU oracle: random irregular matrices (empty rows/columns, ragged layers, repeated
+and missing checks in the layer list), every instantiated kernel shape, extreme priors, tiny and empty batches."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _cmp(H, syn, decType, cuda_device, **kw):
+    from oracle import oracle
+    from qldpcsim_b200.decoders import Decoder
+    okw = dict(kw)
+    want = oracle.Graph(H).decode(decType, syn, **okw)
+    got = Decoder(H, decType, **kw).decode(syn)
+    return want, got
+
+
+def _random_case(rng, m, n, density, max_rw=None):
+    H = (rng.random((m, n)) < density).astype(np.int8)
+    if max_rw:
+        for i in range(m):
+            idx = np.nonzero(H[i])[0]
+            if len(idx) > max_rw:
+                H[i, rng.choice(idx, len(idx) - max_rw, replace=False)] = 0
+    e = (rng.random((200, n)) < 0.08).astype(np.int64)
+    syn = (e @ H.T.astype(np.int64)) % 2
+    return H, syn.astype(np.uint8)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_ms_random_irregular(seed, cuda_device):
+    rng = np.random.default_rng(seed)
+    m, n = int(rng.integers(2, 40)), int(rng.integers(3, 70))
+    H, syn = _random_case(rng, m, n, rng.choice([0.05, 0.15, 0.3]), max_rw=30)
+    # layer list: random contiguous split, sometimes shuffled, sometimes with a check repeated and one left out
+    cuts = sorted(set([0, m] + list(rng.integers(0, m + 1, size=rng.integers(0, 6)))))
+    layers = [np.arange(a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+    if seed % 3 == 1:
+        rng.shuffle(layers)
+    if seed % 3 == 2 and m > 3:
+        layers = layers + [np.array([0, m - 1])]
+        layers[0] = layers[0][1:]
+    if (H.sum(axis=0).max(initial=0) > 16):
+        pytest.skip("column weight above the instantiated kernels")
+    p = float(rng.choice([0.01, 0.1, 0.3]))
+    want, got = _cmp(H, syn, "MS", cuda_device, p=p, max_iter=int(rng.integers(1, 12)), layers=layers)
+    assert np.array_equal(got["e_hat"], want["e_hat"]) and np.array_equal(got["iters"], want["iters"])
+    assert np.array_equal(got["converged"], want["converged"])
+
+
+@pytest.mark.parametrize("rw", [1, 3, 4, 5, 8, 9, 17, 18, 19, 31, 32])
+def test_ms_every_row_weight_shape(rw, cuda_device):
+    """Row weights on both sides of every instantiated DC (4, 8, 18, 32), regular and ragged."""
+    rng = np.random.default_rng(rw)
+    m, n = 12, 96
+    for ragged in (False, True):
+        H = np.zeros((m, n), np.int8)
+        for i in range(m):
+            w = rw if not ragged else int(rng.integers(1, rw + 1))
+            H[i, rng.choice(n, w, replace=False)] = 1
+        e = (rng.random((300, n)) < 0.05).astype(np.int64)
+        syn = ((e @ H.T.astype(np.int64)) % 2).astype(np.uint8)
+        for layers in ([np.arange(m)], [np.arange(0, 5), np.arange(5, 12)], [np.array([i]) for i in range(m)]):
+            want, got = _cmp(H, syn, "MS", cuda_device, p=0.02, max_iter=8, layers=layers)
+            assert np.array_equal(got["e_hat"], want["e_hat"]) and np.array_equal(got["iters"], want["iters"]), (rw, ragged, len(layers))
+
+
+@pytest.mark.parametrize("cw", [1, 4, 5, 6, 9, 10, 16])
+def test_ms_every_column_weight_shape(cw, cuda_device):
+    rng = np.random.default_rng(100 + cw)
+    m, n = 40, 24
+    H = np.zeros((m, n), np.int8)
+    for j in range(n):
+        H[rng.choice(m, cw, replace=False), j] = 1
+    e = (rng.random((200, n)) < 0.1).astype(np.int64)
+    syn = ((e @ H.T.astype(np.int64)) % 2).astype(np.uint8)
+    want, got = _cmp(H, syn, "MS", cuda_device, p=0.05, max_iter=6, layers=[np.arange(0, 20), np.arange(20, 40)])
+    assert np.array_equal(got["e_hat"], want["e_hat"]) and np.array_equal(got["iters"], want["iters"])
+
+
+def test_ms_extreme_priors(cuda_device):
+    """p > 1/2 (negative prior: untouched variables decide 1), p -> 0 (eps clamp), p = 1/2 (zero prior)."""
+    from qldpcsim_b200 import pcmlibrary
+    Hx, _ = pcmlibrary.by_name("LP04_0")
+    rng = np.random.default_rng(3)
+    e = (rng.random((300, Hx.shape[1])) < 0.05).astype(np.int64)
+    syn = ((e @ Hx.T) % 2).astype(np.uint8)
+    from qldpcsim_b200.pcm import layerize
+    lay = layerize(Hx)
+    for p in (0.8, 0.5, 1e-12, 0.0, 0.999999):
+        want, got = _cmp((Hx % 2).astype(np.int8), syn, "MS", cuda_device, p=p, max_iter=5, layers=lay)
+        assert np.array_equal(got["e_hat"], want["e_hat"]) and np.array_equal(got["iters"], want["iters"]), p
+
+
+def test_ms_other_beta_and_max_iter_edge(cuda_device):
+    from qldpcsim_b200 import pcmlibrary
+    Hx, _ = pcmlibrary.by_name("LP04_0")
+    H = (Hx % 2).astype(np.int8)
+    rng = np.random.default_rng(4)
+    e = (rng.random((200, H.shape[1])) < 0.06).astype(np.int64)
+    syn = ((e @ H.T.astype(np.int64)) % 2).astype(np.uint8)
+    for beta, it in ((1.0, 3), (0.5, 1), (0.9, 2)):
+        want, got = _cmp(H, syn, "MS", cuda_device, p=0.02, max_iter=it, layers=[np.arange(H.shape[0])], beta=beta)
+        assert np.array_equal(got["e_hat"], want["e_hat"]) and np.array_equal(got["iters"], want["iters"])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_bp_bf_ng_random_irregular(seed, cuda_device):
+    rng = np.random.default_rng(50 + seed)
+    m, n = int(rng.integers(2, 30)), int(rng.integers(3, 50))
+    H, syn = _random_case(rng, m, n, 0.15, max_rw=30)
+    for dt, kw in (("NG", {}), ("BF", {"max_iter": 50}), ("BF", {"max_iter": 3})):
+        want, got = _cmp(H, syn, dt, cuda_device, **kw)
+        assert np.array_equal(got["e_hat"], want["e_hat"]) and np.array_equal(got["iters"], want["iters"]), dt
+        assert np.array_equal(got["converged"], want["converged"]), dt
+    layers = [np.arange(0, m // 2), np.arange(m // 2, m)]
+    want, got = _cmp(H, syn, "BP", cuda_device, p=0.05, max_iter=6, layers=layers)
+    same = (got["e_hat"] == want["e_hat"]).all(axis=1) & (got["iters"] == want["iters"])
+    assert same.mean() >= 0.99        # tanh/atanh differ in the last ulp between libm and CUDA; tiny random codes are touchy
+
+
+def test_batch_sizes(cuda_device):
+    """0, 1, and a batch that does not fill one CTA; output buffers untouched beyond the batch."""
+    from oracle import oracle
+    from qldpcsim_b200 import pcmlibrary
+    from qldpcsim_b200.decoders import Decoder
+    H = (pcmlibrary.steane_code()[0] % 2).astype(np.int8)
+    d = Decoder(H, "MS", p=0.05, max_iter=50, layers=[np.arange(3)])
+    out = d.decode(np.zeros((0, 3), np.uint8))
+    assert out["e_hat"].shape == (0, 7) and out["iters"].shape == (0,)
+    syn = np.array([[1, 0, 1]], np.uint8)
+    want = oracle.Graph(H).decode("MS", syn, p=0.05, max_iter=50, layers=[np.arange(3)])
+    got = d.decode(syn[0])                                  # 1-D syndrome accepted
+    assert np.array_equal(got["e_hat"], want["e_hat"]) and got["iters"][0] == want["iters"][0]
+    with pytest.raises(ValueError):
+        d.decode(np.zeros((2, 4), np.uint8))                # wrong syndrome length
+
+
+def test_plan_errors(cuda_device):
+    from qldpcsim_b200 import _lib
+    from qldpcsim_b200.decoders import Decoder
+    H = np.zeros((3, 5), np.int8)
+    H[0, :] = 1
+    with pytest.raises(IndexError):
+        Decoder(H, "MS", p=0.1, layers=[np.array([0, 3])])          # check index outside the matrix
+    with pytest.raises(ValueError):
+        Decoder(H, "XX")
+    big = np.ones((40, 40), np.int8)                                 # row weight 40 > 32
+    with pytest.raises(_lib.QldpcError):
+        Decoder(big, "MS", p=0.1, layers=[np.arange(40)])
+
+
+def test_integration_md_stub_runs(cuda_device):
+    """The ctypes binding printed in INTEGRATION.md is executable as written (library path substituted)."""
+    import os
+    import re
+    from conftest import ROOT, load_golden
+    from qldpcsim_b200 import _lib
+    from qldpcsim_b200.pcm import schedule_layers
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.findall(r"```python\n(import ctypes, numpy as np.*?)```", text, flags=re.S)[0]
+    block = block.replace('ctypes.CDLL("libqldpc_b200.so")', f'ctypes.CDLL("{_lib.LIB_PATH}")')
+    ns = {}
+    exec(compile(block, "INTEGRATION.md", "exec"), ns)
+    g = load_golden("LP04_0_MS_L_p05")
+    lX, _ = schedule_layers(g["Hx"], g["Hz"], "L")
+    e, it = ns["decode_batch"](g["Hz"], g["sy_z"], "MS", p=0.05 / 3, max_iter=50, layers=lX)
+    assert np.array_equal(e, g["eX_ref"]) and np.array_equal(it, g["itX"])
+    e, it = ns["decode_batch"](g["Hz"], g["sy_z"], "NG")
+    assert e.shape == g["eX_ref"].shape
