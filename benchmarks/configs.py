@@ -30,7 +30,7 @@ CONFIGS = [
     ("cfg2 LP118_0 BP-F 100it p=.02", "LP118_0", "BP", "F", 0.02, 100, -1, 400_000),
     ("cfg2 LP118_0 BP-F 100it p=.05", "LP118_0", "BP", "F", 0.05, 100, -1, 200_000),
     ("cfg2 LP118_0 BP-F 100it p=.10", "LP118_0", "BP", "F", 0.10, 100, -1, 40_000),
-    ("cfg3 LP118_2 MS-S p=.05", "LP118_2", "MS", "S", 0.05, 50, -1, 100_000),
+    ("cfg3 LP118_2 MS-S p=.05", "LP118_2", "MS", "S", 0.05, 50, -1, 1_000_000),
     ("cfg3 LP118_2 MS-S + OSD-10 p=.05", "LP118_2", "MS", "S", 0.05, 50, 10, 100_000),
     ("LP118_0 MS-L + OSD-0 p=.10", "LP118_0", "MS", "L", 0.10, 50, 0, 200_000),
     ("cfg4 Tanner MS-L p=.03", "T", "MS", "L", 0.03, 50, -1, 400_000),

@@ -66,7 +66,7 @@ typedef struct {
     double  beta;               /* MS normalisation (decoders.py:115), 0.75 in the driver               */
     double  eps;                /* BP clamp shift (decoders.py:195, :257-258)                           */
     int32_t osd_order;          /* OSDorder (decoders.py:116, :194); < 0 disables                       */
-    int32_t reserved;
+    int32_t reserved;           /* min-sum kernel choice: 0 automatic, 1 warp-per-shot, 2 lane-per-shot           */
 } qldpc_opts;
 
 typedef struct qldpc_plan qldpc_plan;
@@ -82,7 +82,7 @@ int qldpc_plan_destroy(qldpc_plan *plan);
 
 /* Plan introspection: what = 0 m, 1 n, 2 nnz, 3 n_layers, 4 CTAs launched, 5 threads per CTA,
  * 6 dynamic shared memory bytes per CTA, 7 shots resident per CTA, 8 max row weight, 9 max column weight,
- * 10 GF(2) rank of H (gf2math.rank, gf2math.py:91-135). */
+ * 10 GF(2) rank of H (gf2math.rank, gf2math.py:91-135), 11 whether the lane-per-shot min-sum kernel is used. */
 int64_t qldpc_plan_info(const qldpc_plan *plan, int what);
 
 /* Decode `shots` syndromes.  Replaces the per-shot calls NG_decoder / BF_decoder / MS_decoder / BP_decoder

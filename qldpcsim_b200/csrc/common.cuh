@@ -77,6 +77,11 @@ struct qldpc_plan {
     // host copies of the graph (CSR / CSC) for the kernels that want int32 tables in global memory
     std::vector<int32_t> row_ptr, col_idx, col_ptr, row_idx, layer_ptr, layer_chk;
     uint16_t *d_blob = nullptr;
+    uint16_t *d_lane_blob = nullptr;   // tables of the lane-per-shot min-sum kernel (serial-like schedules)
+    bool use_lane = false;         // lane kernel available for this plan
+    bool lane_forced = false;      // opts.reserved == 2: use it for every batch size
+    int lane_grid = 0;
+    size_t lane_smem = 0;
     int32_t *d_row_ptr = nullptr, *d_col_idx = nullptr, *d_col_ptr = nullptr, *d_row_idx = nullptr;
     uint32_t *d_hbits = nullptr;   // [m][nw] bit-packed rows of H (OSD, sampler, classification)
     unsigned long long *d_work = nullptr;

@@ -168,3 +168,43 @@ def test_integration_md_stub_runs(cuda_device):
     assert np.array_equal(e, g["eX_ref"]) and np.array_equal(it, g["itX"])
     e, it = ns["decode_batch"](g["Hz"], g["sy_z"], "NG")
     assert e.shape == g["eX_ref"].shape
+
+
+LANE_CASES = [("steane", "S", 0.1, 2000), ("LP04_0", "S", 0.05, 600), ("LP04_0", "L", 0.08, 600), ("LP118_0", "L", 0.05, 400),
+              ("LP118_0", "F", 0.05, 200), ("LP118_2", "S", 0.05, 100), ("bicycle", "L", 0.03, 300), ("T", "S", 0.03, 70)]
+
+
+@pytest.mark.parametrize("code,sched,p,shots", LANE_CASES)
+def test_ms_lane_kernel_matches_oracle(code, sched, p, shots, cuda_device):
+    """The lane-per-shot min-sum kernel (forced) on serial, layered and flooding schedules, incl. llr output and a
+    shot count that leaves lanes idle / forces refills."""
+    from oracle import oracle
+    from qldpcsim_b200 import pcmlibrary, sampler
+    from qldpcsim_b200.decoders import Decoder
+    from qldpcsim_b200.pcm import schedule_layers
+    Hx, Hz = [(h % 2).astype(np.int8) for h in pcmlibrary.by_name(code)]
+    rec = sampler.sample_record(Hx, Hz, p, shots, seed=77)
+    sy_z = rec[:, :Hz.shape[0]]
+    lX, _ = schedule_layers(Hx, Hz, sched)
+    want = oracle.Graph(Hz).decode("MS", sy_z, p=p / 3, max_iter=20, layers=lX, want_posterior=True)
+    d = Decoder(Hz, "MS", p=p / 3, max_iter=20, layers=lX, kernel="lane")
+    assert d.info()["lane_kernel"] == 1
+    got = d.decode(sy_z, want_llr=True)
+    assert np.array_equal(got["e_hat"], want["e_hat"]) and np.array_equal(got["iters"], want["iters"])
+    assert np.array_equal(got["converged"], want["converged"])
+    assert np.array_equal(got["posterior"], want["posterior"])
+    dw = Decoder(Hz, "MS", p=p / 3, max_iter=20, layers=lX, kernel="warp")
+    assert dw.info()["lane_kernel"] == 0
+    gw = dw.decode(sy_z, want_llr=True)
+    assert np.array_equal(gw["e_hat"], want["e_hat"]) and np.array_equal(gw["posterior"], want["posterior"])
+
+
+def test_ms_lane_kernel_with_osd(cuda_device):
+    from conftest import load_golden
+    from qldpcsim_b200.decoders import Decoder
+    from qldpcsim_b200.pcm import schedule_layers
+    g = load_golden("LP04_0_MS_L_OSD0_p10")
+    lX, _ = schedule_layers(g["Hx"], g["Hz"], "L")
+    a = Decoder(g["Hz"], "MS", p=0.1 / 3, max_iter=8, layers=lX, OSDorder=0, kernel="lane").decode(g["sy_z"])
+    b = Decoder(g["Hz"], "MS", p=0.1 / 3, max_iter=8, layers=lX, OSDorder=0, kernel="warp").decode(g["sy_z"])
+    assert np.array_equal(a["e_hat"], b["e_hat"]) and np.array_equal(a["iters"], g["itX"])
