@@ -34,7 +34,7 @@ __host__ __device__ inline BpSmemLayout bp_layout(const Tables &t)
 {
     BpSmemLayout l;
     int o = 0;
-    l.off_c2v = o; o += 8 * t.dc * t.m;
+    l.off_c2v = o; o += 8 * t.dc * t.ms;
     l.off_T = o;   o += 8 * (t.n + 1);
     l.off_par = o; o += 4 * t.mw;
     l.off_syn = o; o += 4 * t.mw;
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint
     double *T = reinterpret_cast<double *>(base + lay.off_T);
     uint32_t *par = reinterpret_cast<uint32_t *>(base + lay.off_par);
     uint32_t *syn = reinterpret_cast<uint32_t *>(base + lay.off_syn);
-    const int m = t.m, n = t.n, dc = t.dc;
+    const int m = t.ms, n = t.n, dc = t.dc;   // m: slot stride
     const double one_m_eps = 1.0 - c.eps;                     // `1-eps` of decoders.py:257
     const bool init_bit = c.L0 < 0.0;
     constexpr int CPP = 32 / LPC;

@@ -38,6 +38,8 @@ struct Tables {
     int off_rowpar;      // [2*mw]   parity of the row weights as bit words (low half, high half)
     int dvs;
     int n_pad;           // n rounded up to a multiple of 32 (first-step variable sweep)
+    int ms;              // slot stride of the slot-major edge arrays (>= m; padded so that the lane groups of the
+                         // min-sum check phase fall on disjoint shared-memory banks)
     int len;             // blob length in uint16 units (padded to a multiple of 8)
 };
 
@@ -84,6 +86,7 @@ struct qldpc_plan {
     size_t lane_smem = 0;
     int32_t *d_row_ptr = nullptr, *d_col_idx = nullptr, *d_col_ptr = nullptr, *d_row_idx = nullptr;
     uint32_t *d_hbits = nullptr;   // [m][nw] bit-packed rows of H (OSD, sampler, classification)
+    uint32_t *d_hcol = nullptr;    // [n][mw] bit-packed columns of H (syndrome of a sparse vector)
     unsigned long long *d_work = nullptr;
     int *d_fail_count = nullptr;
     int sm_count = 0;

@@ -149,22 +149,35 @@ __global__ void __launch_bounds__(256) ng_decode_kernel(GraphDev g, DecodeIO io)
 struct ClassifyArgs {
     GraphDev gz, gx;                       // gz = Hz (X-error decode), gx = Hx (Z-error decode)
     const uint32_t *colmask_z, *colmask_x; // [nw] OR of the rows of Hz / Hx
+    const uint32_t *hcol_z, *hcol_x;       // [n][mw] bit-packed columns of Hz / Hx
     const uint32_t *errx, *errz, *ehx, *ehz, *synz, *synx;
     const int32_t *itx, *itz;
     long long shots;
     unsigned long long *counters;
 };
 
-__device__ __forceinline__ bool syndrome_mismatch(const GraphDev &g, const uint32_t *e /*global [nw]*/,
+// H e (mod 2) by XOR-ing the bit-packed COLUMNS of H selected by the set bits of e (the estimates are sparse: ~2pn/3
+// bits), one syndrome word per lane; returns whether it differs from `syn`.  hcol: [n][mw] words.  Needs mw <= 32.
+__device__ __forceinline__ bool syndrome_mismatch(const GraphDev &g, const uint32_t *__restrict__ hcol, const uint32_t *e /*global [nw]*/,
                                                   const uint32_t *syn /*global [mw]*/, int lane)
 {
-    bool bad = false;
-    for (int i = lane; i < g.m; i += 32) {
-        uint32_t par = 0;
-        for (int x = g.row_ptr[i]; x < g.row_ptr[i + 1]; ++x) par ^= get_bit(e, g.col_idx[x]);
-        bad |= par != get_bit(syn, i);
+    uint32_t acc = (lane < g.mw) ? syn[lane] : 0u;
+    const uint32_t mine = (lane < g.nw) ? e[lane] : 0u;
+    for (int w0 = 0; w0 < g.nw; w0 += 32) {
+        const uint32_t word_l = (w0 == 0) ? mine : ((w0 + lane < g.nw) ? e[w0 + lane] : 0u);
+        uint32_t nz = __ballot_sync(0xffffffffu, word_l != 0u);
+        while (nz) {                                        // warp-uniform loops: words, then their set bits
+            const int wl = __ffs(nz) - 1;
+            nz &= nz - 1;
+            uint32_t bits = __shfl_sync(0xffffffffu, word_l, wl);
+            while (bits) {
+                const int j = (w0 + wl) * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                if (lane < g.mw) acc ^= hcol[(size_t)j * g.mw + lane];
+            }
+        }
     }
-    return __any_sync(0xffffffffu, bad);
+    return __any_sync(0xffffffffu, acc != 0u);
 }
 
 __global__ void __launch_bounds__(256) classify_kernel(ClassifyArgs a)
@@ -187,8 +200,8 @@ __global__ void __launch_bounds__(256) classify_kernel(ClassifyArgs a)
         }
         const bool exact = !__any_sync(0xffffffffu, diff);
         const bool degen = !exact && !__any_sync(0xffffffffu, touch);
-        const bool fx = syndrome_mismatch(a.gz, hx, a.synz + s * a.gz.mw, lane);
-        const bool fz = syndrome_mismatch(a.gx, hz, a.synx + s * a.gx.mw, lane);
+        const bool fx = syndrome_mismatch(a.gz, a.hcol_z, hx, a.synz + s * a.gz.mw, lane);
+        const bool fz = syndrome_mismatch(a.gx, a.hcol_x, hz, a.synx + s * a.gx.mw, lane);
         if (lane == 0) {
             c_fx += fx; c_fz += fz; c_ex += exact; c_dg += degen;
             c_ix += (unsigned long long)a.itx[s]; c_iz += (unsigned long long)a.itz[s]; c_sh += 1;

@@ -38,7 +38,7 @@ constexpr int kMsMaxWarps = 24;   // 768 threads per CTA -> up to 85 registers p
 
 struct MsSmemLayout {
     // per-shot state, offsets in bytes from the warp's base
-    int off_c2v;   // float [dc*m + 4]  (entry dc*m is the always-zero slot)
+    int off_c2v;   // float [dc*ms + 4]  (ms = padded slot stride; entry dc*ms is the always-zero slot)
     int off_S;     // float [n + 1] (entry n: dummy variable of the padded lists)
     int off_par;   // uint32 [mw]
     int off_syn;   // uint32 [mw]
@@ -49,7 +49,7 @@ __host__ __device__ inline MsSmemLayout ms_layout(const Tables &t)
 {
     MsSmemLayout l;
     int o = 0;
-    l.off_c2v = o; o += 4 * (t.dc * t.m + 4);
+    l.off_c2v = o; o += 4 * (t.dc * t.ms + 4);
     o = (o + 15) & ~15;
     l.off_S = o;   o += 4 * (t.n + 1);
     l.off_par = o; o += 4 * t.mw;
@@ -93,8 +93,8 @@ struct MsAddr {          // shared-window byte addresses, warp-uniform
     uint32_t var_tab;    // uint16 [dc*m]   (CTA tables)
     uint32_t layer_chk;  // uint16 [...]
     uint32_t c2v, S, par, syn;   // per-warp state
-    uint32_t m2;         // 2*m : byte stride of one slot row in var_tab
-    uint32_t m4;         // 4*m : byte stride of one slot row in c2v
+    uint32_t m2;         // 2*ms : byte stride of one slot row in var_tab
+    uint32_t m4;         // 4*ms : byte stride of one slot row in c2v
 };
 
 // Check-node phase of one layer with LPC lanes per check (decoders.py:156-169).
@@ -258,8 +258,8 @@ __global__ void __launch_bounds__(kMsMaxWarps * 32, 1) ms_decode_kernel(Tables t
     A.S = wbase + lay.off_S;
     A.par = wbase + lay.off_par;
     A.syn = wbase + lay.off_syn;
-    A.m2 = 2u * t.m;
-    A.m4 = 4u * t.m;
+    A.m2 = 2u * t.ms;
+    A.m4 = 4u * t.ms;
     const uint32_t col_ptr = tab + 2u * t.off_col_ptr, col_chk = tab + 2u * t.off_col_chk;
     const uint32_t layer_ptr = tab + 2u * t.off_layer_ptr, layer_lpc = tab + 2u * t.off_layer_lpc;
     const uint32_t lvar_ptr = tab + 2u * t.off_lvar_ptr, lvar_idx = tab + 2u * t.off_lvar_idx;
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(kMsMaxWarps * 32, 1) ms_decode_kernel(Tables t
     const int n = t.n;
     const float Tf = c.Tf;
     const bool init_bit = 0.0f < Tf;                    // decision of a variable whose sum is still 0 (only if L < 0)
-    const int c2v_words = t.dc * t.m + 4;
+    const int c2v_words = t.dc * t.ms + 4;
 
     for (;;) {
         long long shot = 0;

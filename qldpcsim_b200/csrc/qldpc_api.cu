@@ -218,6 +218,10 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
                 hb[(size_t)m * t.nw + (j >> 5)] |= 1u << (j & 31);
             }
         if ((rc = upload(&p->d_hbits, hb))) { qldpc_plan_destroy(p); return rc; }
+        std::vector<uint32_t> hc((size_t)n * t.mw, 0u);
+        for (int i = 0; i < m; ++i)
+            for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x) hc[(size_t)p->col_idx[x] * t.mw + (i >> 5)] |= 1u << (i & 31);
+        if ((rc = upload(&p->d_hcol, hc))) { qldpc_plan_destroy(p); return rc; }
         // GF(2) rank of H (gf2math.py:91-135) by bit-packed elimination on the host; OSD stops its column walk there
         std::vector<uint32_t> w(hb.begin(), hb.begin() + (size_t)m * t.nw);
         int r = 0;
@@ -249,25 +253,30 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
         std::vector<uint16_t> &b = p->h_blob;
         auto put = [&](int count) { int off = (int)b.size(); b.resize(b.size() + count, 0); return off; };
         const bool is_ms = o->dec_type == QLDPC_MS;
+        int ms = m;
         int dc_inst = 0, dv_inst = 0;
         if (is_ms) {
             pk->ms = ms_select(dc, dv, regular, &dc_inst, &dv_inst);
             if (!pk->ms) return bail(QLDPC_ETOOBIG, "min-sum kernels are instantiated for row weight <= 32 and column weight <= 16");
             dc = dc_inst;              // slot-major tables are padded to the instantiated row weight
             t.dc = dc;
-            if ((long long)dc * m * 4 + 4 > 65535 || (long long)n * 4 > 65535)
+            // slot stride: with LPC lanes per check, lane h starts at slot h*SPL, i.e. SPL*ms words further; ms = 4 (mod 8)
+            // puts the two halves of the common 2-lane split 16 banks apart (m = 240 would put them on the same banks)
+            while (ms % 8 != 4) ++ms;
+            if ((long long)dc * ms * 4 + 4 > 65535 || (long long)n * 4 > 65535)
                 return bail(QLDPC_ETOOBIG, "code too large for the 16-bit shared-memory offset tables (need 4*m*row_weight < 65532, 4*n < 65536)");
         }
-        t.off_var = put(dc * m);
-        std::fill(b.begin() + t.off_var, b.begin() + t.off_var + dc * m, kPad);
+        t.ms = ms;
+        t.off_var = put(dc * ms);
+        std::fill(b.begin() + t.off_var, b.begin() + t.off_var + dc * ms, kPad);
         for (int i = 0; i < m; ++i)
-            for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x) b[t.off_var + (x - p->row_ptr[i]) * m + i] = (uint16_t)(4 * p->col_idx[x]);
+            for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x) b[t.off_var + (x - p->row_ptr[i]) * ms + i] = (uint16_t)(4 * p->col_idx[x]);
         t.off_col_ptr = put(n + 1);
         for (int j = 0; j <= n; ++j) b[t.off_col_ptr + j] = (uint16_t)p->col_ptr[j];
         t.off_col_pos = put(E);
         t.off_col_chk = put(E);
         for (int x = 0; x < E; ++x) {
-            b[t.off_col_pos + x] = (uint16_t)(col_slot[x] * m + p->row_idx[x]);
+            b[t.off_col_pos + x] = (uint16_t)(col_slot[x] * ms + p->row_idx[x]);
             b[t.off_col_chk + x] = (uint16_t)p->row_idx[x];
         }
         // min-sum variable-phase table: per variable dvs byte offsets into c2v, padded with the zero slot
@@ -279,9 +288,9 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             for (int j = 0; j < n; ++j)
                 for (int x = 0; x < t.dvs; ++x) {
                     const int e = p->col_ptr[j] + x;
-                    b[t.off_vn + j * t.dvs + x] = (uint16_t)(e < p->col_ptr[j + 1] ? 4 * (col_slot[e] * m + p->row_idx[e]) : 4 * dc * m);
+                    b[t.off_vn + j * t.dvs + x] = (uint16_t)(e < p->col_ptr[j + 1] ? 4 * (col_slot[e] * ms + p->row_idx[e]) : 4 * dc * ms);
                 }
-        if (is_ms) for (int x = 0; x < t.dvs; ++x) b[t.off_vn + n * t.dvs + x] = (uint16_t)(4 * dc * m);   // dummy variable n
+        if (is_ms) for (int x = 0; x < t.dvs; ++x) b[t.off_vn + n * t.dvs + x] = (uint16_t)(4 * dc * ms);   // dummy variable n
         t.off_rowpar = put(2 * t.mw);
         for (int i = 0; i < m; ++i)
             if ((p->row_ptr[i + 1] - p->row_ptr[i]) & 1) b[t.off_rowpar + 2 * (i >> 5) + ((i & 31) >> 4)] |= (uint16_t)(1u << (i & 15));
@@ -441,7 +450,7 @@ int qldpc_plan_destroy(qldpc_plan *p)
     if (!p) return QLDPC_OK;
     cudaSetDevice(p->device);
     cudaFree(p->d_blob); cudaFree(p->d_lane_blob); cudaFree(p->d_row_ptr); cudaFree(p->d_col_idx); cudaFree(p->d_col_ptr); cudaFree(p->d_row_idx);
-    cudaFree(p->d_hbits); cudaFree(p->d_work); cudaFree(p->d_fail_count);
+    cudaFree(p->d_hbits); cudaFree(p->d_hcol); cudaFree(p->d_work); cudaFree(p->d_fail_count);
     for (int s = 0; s < 7; ++s) if (p->scratch[s]) cudaFree(p->scratch[s]);
     delete kernels_of(p);
     for (int s = 0; s < 3; ++s) if (p->streams[s]) cudaStreamDestroy(p->streams[s]);
@@ -656,6 +665,8 @@ int qldpc_classify(const qldpc_plan *px, const qldpc_plan *pz, const uint32_t *e
     a.gz = graph_dev(px); a.gx = graph_dev(pz);
     a.colmask_z = px->d_hbits + (size_t)px->tab.m * px->tab.nw;
     a.colmask_x = pz->d_hbits + (size_t)pz->tab.m * pz->tab.nw;
+    a.hcol_z = px->d_hcol; a.hcol_x = pz->d_hcol;
+    if (px->tab.mw > 32 || pz->tab.mw > 32) return fail(QLDPC_ETOOBIG, "classification supports up to 1024 checks per matrix");
     a.errx = errx; a.errz = errz; a.ehx = ehx; a.ehz = ehz; a.synz = synz; a.synx = synx; a.itx = itx; a.itz = itz;
     a.shots = shots;
     a.counters = reinterpret_cast<unsigned long long *>(counters);
