@@ -37,7 +37,7 @@ struct Tables {
                          //          the offset of the always-zero slot 4*dc*m; dvs = 4, 8 or 16 (min-sum only)
     int off_rowpar;      // [2*mw]   parity of the row weights as bit words (low half, high half)
     int dvs;
-    int n_pad;           // n rounded up to a multiple of 32 (first-step variable sweep)
+    int n_pad;           // n rounded up to a multiple of 64 (first-step variable sweep, two variables per lane and trip)
     int ms;              // slot stride of the slot-major edge arrays (>= m; padded so that the lane groups of the
                          // min-sum check phase fall on disjoint shared-memory banks)
     int len;             // blob length in uint16 units (padded to a multiple of 8)
@@ -62,6 +62,8 @@ struct MsConst {
     double L;        // prior LLR, binary64 (decoders.py:147)
     double Lf;       // (double)(float)L : the prior as first stored into the binary32 v2c array (decoders.py:148-149)
     double beta;     // normalisation (decoders.py:115)
+    double abeta;    // |beta|
+    uint32_t sgn;    // 0x80000000 if beta < 0 (extra sign of every check-to-variable message), else 0
     float Tf;        // -L rounded UP to binary32: fl64(L + S) < 0  <=>  S < Tf for binary32 S
     int max_iter;
 };

@@ -68,27 +68,6 @@ __device__ __forceinline__ uint2 sld_v2(uint32_t a) { uint2 v; asm volatile("ld.
 __device__ __forceinline__ uint4 sld_v4(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t satom_xor(uint32_t a, uint32_t v) { uint32_t o; asm volatile("atom.shared.xor.b32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o; }
 
-struct CnPartial {
-    double m1, m2;   // smallest / second smallest |v2c| over the lane's slots (inf if none)
-    int k1;          // slot of the first minimum
-    uint32_t par;    // parity of the negative signs
-};
-
-// Merge two partial scans of disjoint slot sets.  Symmetric and branch-free on purpose (a lane-parity branch here
-// splits the warp): the winner is the smaller first minimum, ties go to the lower slot, which preserves np.argmin's
-// "first minimum" (decoders.py:161); the new second minimum is the smaller of the loser's first and the winner's
-// second minimum.
-__device__ __forceinline__ void cn_merge(CnPartial &a, const CnPartial &b)
-{
-    const bool lt = (b.m1 < a.m1) | ((b.m1 == a.m1) & (b.k1 < a.k1));
-    const double loser = lt ? a.m1 : b.m1;
-    const double keep = lt ? b.m2 : a.m2;
-    a.m2 = (loser < keep) ? loser : keep;
-    a.m1 = lt ? b.m1 : a.m1;
-    a.k1 = lt ? b.k1 : a.k1;
-    a.par ^= b.par;
-}
-
 struct MsAddr {          // shared-window byte addresses, warp-uniform
     uint32_t var_tab;    // uint16 [dc*m]   (CTA tables)
     uint32_t layer_chk;  // uint16 [...]
@@ -98,72 +77,74 @@ struct MsAddr {          // shared-window byte addresses, warp-uniform
 };
 
 // Check-node phase of one layer with LPC lanes per check (decoders.py:156-169).
+//
+// The reference takes min1 / min2 of a_k = |v2c_k| in binary64 and stores c2v_k = +-fl32(fl64(beta * (a_k == min1 ? min2 : min1))).
+// g(a) = fl32(fl64(beta * a)) is monotone non-decreasing for beta >= 0, so with b_k = g(a_k):  g(min1) = min_k b_k,  and the
+// value handed to an edge with a_k == min1, g(min2) = g(min_{k != first argmin} a_k), equals the second smallest b (counted
+// with multiplicity): if the minimum of b is attained once, it is attained at the unique argmin of a; if it is attained
+// several times, min2_b == min1_b and every edge receives the same magnitude whichever way a_k == min1 falls.  Edges with
+// a_k != min1 receive g(min1) = min1_b, and b_k != min1_b implies a_k != min1.  Hence the rule "magnitude = (b_k == min1_b ?
+// min2_b : min1_b)" on the ROUNDED per-edge values is bit-identical to the reference, needs no argmin index, and the
+// min / second-min / merge logic becomes binary32 FMNMX instead of binary64 compare+select chains.  The sign of b_k is the
+// sign of v2c_k (v2c is never -0.0: it is a difference of which the minuend is never -0.0, and rounding keeps signs).
+// beta < 0 is handled by the caller passing |beta| and folding the extra sign into `sgn_extra`.
 template <int DC, bool REGULAR, int LPC>
-__device__ __forceinline__ void ms_check_phase(int qb, int qe, int lane, const MsAddr &A, double prior, double beta)
+__device__ __forceinline__ void ms_check_phase(int qb, int qe, int lane, const MsAddr &A, double prior, double beta, uint32_t sgn_extra)
 {
     constexpr int SPL = (DC + LPC - 1) / LPC;       // slots per lane
     constexpr int CPP = 32 / LPC;                   // checks per pass
     constexpr bool EXACT = (LPC * SPL == DC);       // no lane owns a slot >= DC
     const int h = lane % LPC;                       // which slice of the row
     const int k0 = h * SPL;                         // first slot of the lane
-    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    const float inf = __int_as_float(0x7f800000);
     for (int q0 = qb; q0 < qe; q0 += CPP) {
         const int q = q0 + lane / LPC;
         const bool act = q < qe;
         const uint32_t i = sld_u16(A.layer_chk + 2u * (uint32_t)(act ? q : qb));
-        const uint32_t vt = A.var_tab + (uint32_t)k0 * A.m2 + 2u * i;    // &var_tab[k0*m + i]
-        const uint32_t cv = A.c2v + (uint32_t)k0 * A.m4 + 4u * i;        // &c2v[k0*m + i]
-        CnPartial pr;
-        pr.m1 = inf; pr.m2 = inf; pr.k1 = 0; pr.par = 0u;
-        uint32_t sb = 0;                            // sign bits of the lane's own slots
+        const uint32_t vt = A.var_tab + (uint32_t)k0 * A.m2 + 2u * i;    // &var_tab[k0*ms + i]
+        const uint32_t cv = A.c2v + (uint32_t)k0 * A.m4 + 4u * i;        // &c2v[k0*ms + i]
+        float bs[SPL];                              // signed b_k of the lane's own slots
+        float m1 = inf, m2 = inf;                   // smallest / second smallest |b| (inf if none)
+        uint32_t px = 0;                            // xor of the b_k bit patterns: bit 31 = parity of the negative signs
 #pragma unroll
         for (int s = 0; s < SPL; ++s) {
+            bs[s] = 0.0f;
             if (EXACT || k0 + s < DC) {
                 const uint32_t joff = sld_u16(vt + (uint32_t)s * A.m2);       // byte offset of S_j, kPad past a short row
                 if (REGULAR || joff != kPad) {
                     const double post = __dadd_rn(prior, (double)sld_f32(A.S + joff));                   // :173
                     const double v = __dsub_rn(post, (double)sld_f32(cv + (uint32_t)s * A.m4));          // :177
-                    const double av = fabs(v);
-                    const uint32_t neg = v < 0.0 ? 1u : 0u;                                   // :157-158 (0 -> +1)
-                    sb |= neg << s;
-                    pr.par ^= neg;
-                    const bool lt1 = av < pr.m1, lt2 = av < pr.m2;                            // selects, not branches
-                    pr.m2 = lt1 ? pr.m1 : (lt2 ? av : pr.m2);                                 // min over the others (:162-164)
-                    pr.m1 = lt1 ? av : pr.m1;                                                 // first argmin (:161)
-                    pr.k1 = lt1 ? (k0 + s) : pr.k1;
+                    const float b = __double2float_rn(__dmul_rn(beta, v));                               // :167-168 (f64 product, f32 store)
+                    bs[s] = b;
+                    px ^= __float_as_uint(b);                                                             // :157-159
+                    const float ab = fabsf(b);
+                    m2 = fminf(m2, fmaxf(m1, ab));                                                        // :162-164
+                    m1 = fminf(m1, ab);                                                                   // :160
                 }
             }
         }
         // butterfly over the LPC lanes of the check
 #pragma unroll
         for (int d = 1; d < LPC; d <<= 1) {
-            CnPartial o;
-            o.m1 = __shfl_xor_sync(0xffffffffu, pr.m1, d);
-            o.m2 = __shfl_xor_sync(0xffffffffu, pr.m2, d);
-            const uint32_t pk = __shfl_xor_sync(0xffffffffu, (uint32_t)pr.k1 | (pr.par << 8), d);
-            o.k1 = (int)(pk & 0xffu);
-            o.par = pk >> 8;
-            cn_merge(pr, o);
+            const float o1 = __shfl_xor_sync(0xffffffffu, m1, d);
+            const float o2 = __shfl_xor_sync(0xffffffffu, m2, d);
+            px ^= __shfl_xor_sync(0xffffffffu, px, d);
+            m2 = fminf(fmaxf(m1, o1), fminf(m2, o2));
+            m1 = fminf(m1, o1);
         }
         if (act) {
-            // inf -> 0 for an empty / single-edge row (:165-166); f64 product, f32 store (:167-168); an overflowed
-            // binary32 message is zeroed (:169)
-            const double m1 = (pr.m1 == inf) ? 0.0 : pr.m1;
-            const double m2 = (pr.m2 == inf) ? 0.0 : pr.m2;
-            float r1 = __double2float_rn(__dmul_rn(beta, m1));
-            float r2 = __double2float_rn(__dmul_rn(beta, m2));
-            r1 = (fabsf(r1) == __int_as_float(0x7f800000)) ? 0.0f : r1;
-            r2 = (fabsf(r2) == __int_as_float(0x7f800000)) ? 0.0f : r2;
+            // inf -> 0: an empty / single-edge row (:165-166) or an overflowed binary32 message (:169)
+            const float r1 = (m1 == inf) ? 0.0f : m1;
+            const float r2 = (m2 == inf) ? 0.0f : m2;
             const uint32_t synbit = (sld_u32(A.syn + 4u * (i >> 5)) >> (i & 31u)) & 1u;
-            const uint32_t P = pr.par ^ synbit;                                               // sign product x syndrome sign (:151,:159)
-            const int kk = pr.k1 - k0;                                                        // local slot of the minimum (if mine)
+            const uint32_t P = (px ^ (synbit << 31) ^ sgn_extra) & 0x80000000u;               // sign product x syndrome sign (:151,:159)
+            const uint32_t r1s = __float_as_uint(r1) | P, r2s = __float_as_uint(r2) | P;
 #pragma unroll
             for (int s = 0; s < SPL; ++s) {
                 if (EXACT || k0 + s < DC) {
                     if (REGULAR || sld_u16(vt + (uint32_t)s * A.m2) != kPad) {
-                        const float mag = (s == kk) ? r2 : r1;
-                        const uint32_t bits = __float_as_uint(mag) ^ ((((sb >> s) & 1u) ^ P) << 31);
-                        sst_f32(cv + (uint32_t)s * A.m4, __uint_as_float(bits));
+                        const uint32_t mag = (fabsf(bs[s]) == m1) ? r2s : r1s;
+                        sst_u32(cv + (uint32_t)s * A.m4, mag ^ (__float_as_uint(bs[s]) & 0x80000000u));
                     }
                 }
             }
@@ -207,18 +188,10 @@ __device__ __forceinline__ float ms_colsum(uint32_t c2v, uint32_t vrow)
     return s;
 }
 
-// One variable-node pass over variable j of every lane: new sum, store, flip detection and cooperative parity update.
-template <int DV>
-__device__ __forceinline__ void ms_var_update(uint32_t j, int lane, const MsAddr &A, uint32_t vn_tab, uint32_t col_ptr,
-                                              uint32_t col_chk, float Tf, int &delta)
+// Cooperative parity update for the variables whose hard decision flipped (rare; one flipped variable per trip).
+__device__ __forceinline__ void ms_apply_flips(uint32_t flips, uint32_t j, int lane, const MsAddr &A, uint32_t col_ptr, uint32_t col_chk, int &delta)
 {
-    constexpr int DVS = VnRow<DV>::DVS;
-    const uint32_t sa = A.S + 4u * j;
-    const float s_old = sld_f32(sa);
-    const float s = ms_colsum<DV>(A.c2v, vn_tab + (uint32_t)(2 * DVS) * j);
-    sst_f32(sa, s);
-    uint32_t flips = __ballot_sync(0xffffffffu, (s < Tf) != (s_old < Tf));     // hard decision flipped (:173-174)
-    while (flips) {                                                              // rare; one flipped variable per trip
+    while (flips) {
         const int src = __ffs(flips) - 1;
         flips &= flips - 1;
         const uint32_t jf = __shfl_sync(0xffffffffu, j, src);
@@ -230,6 +203,27 @@ __device__ __forceinline__ void ms_var_update(uint32_t j, int lane, const MsAddr
             const uint32_t old = satom_xor(A.par + 4u * (ch >> 5), bit);
             delta += (old & bit) ? -1 : 1;
         }
+    }
+}
+
+// One variable-node pass over TWO variables per lane (two independent load / add chains in flight): new sums, stores,
+// flip detection.  Lists are padded to a multiple of 64 with the dummy variable n.
+template <int DV>
+__device__ __forceinline__ void ms_var_update2(uint32_t ja, uint32_t jb, int lane, const MsAddr &A, uint32_t vn_tab, uint32_t col_ptr,
+                                               uint32_t col_chk, float Tf, int &delta)
+{
+    constexpr int DVS = VnRow<DV>::DVS;
+    const uint32_t sa = A.S + 4u * ja, sb = A.S + 4u * jb;
+    const float a_old = sld_f32(sa), b_old = sld_f32(sb);
+    const float a = ms_colsum<DV>(A.c2v, vn_tab + (uint32_t)(2 * DVS) * ja);
+    const float b = ms_colsum<DV>(A.c2v, vn_tab + (uint32_t)(2 * DVS) * jb);
+    sst_f32(sa, a);
+    sst_f32(sb, b);
+    const uint32_t fa = __ballot_sync(0xffffffffu, (a < Tf) != (a_old < Tf));   // hard decision flipped (:173-174)
+    const uint32_t fb = __ballot_sync(0xffffffffu, (b < Tf) != (b_old < Tf));
+    if (fa | fb) {
+        ms_apply_flips(fa, ja, lane, A, col_ptr, col_chk, delta);
+        ms_apply_flips(fb, jb, lane, A, col_ptr, col_chk, delta);
     }
 }
 
@@ -297,11 +291,11 @@ __global__ void __launch_bounds__(kMsMaxWarps * 32, 1) ms_decode_kernel(Tables t
             // phase visits EVERY variable (the reference recomputes all posteriors; a variable outside layer 0 has
             // posterior L, which may be negative for p > 1/2)
             const int qb = sld_u16(layer_ptr), qe = sld_u16(layer_ptr + 2u);
-            ms_check_phase<DC, REGULAR, 1>(qb, qe, lane, A, c.Lf, c.beta);
+            ms_check_phase<DC, REGULAR, 1>(qb, qe, lane, A, c.Lf, c.abeta, c.sgn);
             __syncwarp();
             int delta = 0;
-            for (int q = lane; q < t.n_pad; q += 32)
-                ms_var_update<DV>((uint32_t)(q < n ? q : n), lane, A, vn_tab, col_ptr, col_chk, Tf, delta);
+            for (int q = lane; q < t.n_pad; q += 64)
+                ms_var_update2<DV>((uint32_t)(q < n ? q : n), (uint32_t)(q + 32 < n ? q + 32 : n), lane, A, vn_tab, col_ptr, col_chk, Tf, delta);
             unsat += __reduce_add_sync(full, delta);
             __syncwarp();
             converged = unsat == 0;
@@ -311,17 +305,17 @@ __global__ void __launch_bounds__(kMsMaxWarps * 32, 1) ms_decode_kernel(Tables t
                 // ---------------- check-node phase (decoders.py:156-169)
                 const int qb = sld_u16(layer_ptr + 2u * l), qe = sld_u16(layer_ptr + 2u * l + 2u);
                 const int lpc = sld_u16(layer_lpc + 2u * l);
-                if (lpc == 1) ms_check_phase<DC, REGULAR, 1>(qb, qe, lane, A, c.L, c.beta);
-                else if (lpc == 2) ms_check_phase<DC, REGULAR, 2>(qb, qe, lane, A, c.L, c.beta);
-                else if (lpc == 4) ms_check_phase<DC, REGULAR, 4>(qb, qe, lane, A, c.L, c.beta);
-                else ms_check_phase<DC, REGULAR, 8>(qb, qe, lane, A, c.L, c.beta);
+                if (lpc == 1) ms_check_phase<DC, REGULAR, 1>(qb, qe, lane, A, c.L, c.abeta, c.sgn);
+                else if (lpc == 2) ms_check_phase<DC, REGULAR, 2>(qb, qe, lane, A, c.L, c.abeta, c.sgn);
+                else if (lpc == 4) ms_check_phase<DC, REGULAR, 4>(qb, qe, lane, A, c.L, c.abeta, c.sgn);
+                else ms_check_phase<DC, REGULAR, 8>(qb, qe, lane, A, c.L, c.abeta, c.sgn);
                 __syncwarp();
                 // ---------------- variable-node phase (decoders.py:172-174) on the variables whose sums changed.  Every
-                // lane runs the same number of trips (lists are padded to a multiple of 32 with the dummy variable n).
+                // lane runs the same number of trips (lists are padded to a multiple of 64 with the dummy variable n).
                 const int vb = sld_u16(lvar_ptr + 2u * l), ve = sld_u16(lvar_ptr + 2u * l + 2u);
                 int delta = 0;
-                for (int q = vb + lane; q < ve; q += 32)
-                    ms_var_update<DV>(sld_u16(lvar_idx + 2u * q), lane, A, vn_tab, col_ptr, col_chk, Tf, delta);
+                for (int q = vb + lane; q < ve; q += 64)
+                    ms_var_update2<DV>(sld_u16(lvar_idx + 2u * q), sld_u16(lvar_idx + 2u * q + 64u), lane, A, vn_tab, col_ptr, col_chk, Tf, delta);
                 unsat += __reduce_add_sync(full, delta);
                 __syncwarp();
                 // ---------------- H e == syndrome ?  (decoders.py:175-176)

@@ -283,7 +283,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
         t.dvs = is_ms ? (dv_inst <= 4 ? 4 : (dv_inst <= 8 ? 8 : 16)) : 0;
         b.resize((b.size() + 7) & ~size_t(7), 0);              // 16-byte aligned rows
         t.off_vn = put((n + 1) * t.dvs);
-        t.n_pad = (n + 31) & ~31;
+        t.n_pad = (n + 63) & ~63;
         if (is_ms)
             for (int j = 0; j < n; ++j)
                 for (int x = 0; x < t.dvs; ++x) {
@@ -319,7 +319,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             }
             std::sort(vs.begin(), vs.end());
             for (int v : vs) { seen[v] = 0; lvar.push_back((uint16_t)v); }
-            while (lvar.size() % 32) lvar.push_back((uint16_t)n);   // dummy variable n: uniform trip count per lane
+            while (lvar.size() % 64) lvar.push_back((uint16_t)n);   // dummy variable n: uniform trip count per lane
             lvar_ptr[l + 1] = (int)lvar.size();
         }
         if (lvar.size() > 65535) return bail(QLDPC_ETOOBIG, "per-layer variable lists exceed 65535 entries");
@@ -495,7 +495,7 @@ static int launch_decode(qldpc_plan *p, const uint32_t *syn, int64_t shots, uint
     switch (o.dec_type) {
     case QLDPC_MS: {
         MsConst c;
-        c.L = o.prior_llr; c.Lf = (double)(float)o.prior_llr; c.beta = o.beta; c.max_iter = o.max_iter;
+        c.L = o.prior_llr; c.Lf = (double)(float)o.prior_llr; c.beta = o.beta; c.abeta = std::fabs(o.beta); c.sgn = std::signbit(o.beta) ? 0x80000000u : 0u; c.max_iter = o.max_iter;
         {   // smallest binary32 >= -L
             const double T = -o.prior_llr;
             float f = (float)T;
