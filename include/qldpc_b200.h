@@ -82,7 +82,9 @@ int qldpc_plan_destroy(qldpc_plan *plan);
 
 /* Plan introspection: what = 0 m, 1 n, 2 nnz, 3 n_layers, 4 CTAs launched, 5 threads per CTA,
  * 6 dynamic shared memory bytes per CTA, 7 shots resident per CTA, 8 max row weight, 9 max column weight,
- * 10 GF(2) rank of H (gf2math.rank, gf2math.py:91-135), 11 whether the lane-per-shot min-sum kernel is used. */
+ * 10 GF(2) rank of H (gf2math.rank, gf2math.py:91-135), 11 whether the lane-per-shot min-sum kernel is used,
+ * 12 / 13 shared-memory wavefronts per iteration modelled by the min-sum layout planner / its conflict-free bound,
+ * 14 bytes of shared-memory state per shot. */
 int64_t qldpc_plan_info(const qldpc_plan *plan, int what);
 
 /* Decode `shots` syndromes.  Replaces the per-shot calls NG_decoder / BF_decoder / MS_decoder / BP_decoder

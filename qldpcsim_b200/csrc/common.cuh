@@ -97,6 +97,7 @@ struct qldpc_plan {
     int grid = 0, threads = 0, shots_per_cta = 0;
     size_t smem_bytes = 0;
     size_t state_bytes = 0;        // per-shot shared-memory state
+    long long plan_wavefronts = 0, plan_wavefronts_ideal = 0;   // min-sum layout planner: modelled / conflict-free wavefronts per iteration
     // scratch for qldpc_decode_host / OSD
     void *scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -4,17 +4,24 @@
 // in oracle/qldpc_oracle.c:ms_decode_one).  Mapping:
 //   * one WARP owns one shot from its first layer step to its exit and then pulls the next shot from a
 //     global dispenser (shots converge after 1..max_iter iterations, so there are no lock-step batches);
-//   * the whole message state of the shot lives in shared memory: c2v as binary32 per edge (slot-major: the
-//     k-th edge of check i at k*m+i), the binary32 column sums S_j, the residual syndrome H e + s as bit words;
+//   * the whole message state of the shot lives in shared memory: c2v as binary32 per edge, the binary32
+//     column sums S_j, the residual syndrome H e + s as bit words;
+//   * VARIABLE-MAJOR message layout.  Variables are renumbered by descending column weight (stable, so the
+//     circulant blocks of a lifted code stay contiguous); the x-th check-to-variable message of variable j'
+//     (ascending check order, the order of the reference's np.sum, decoders.py:172) lives at word
+//     coff[x] + j' of the c2v array ("region x" holds the cnt[x] variables of degree > x).  The variable
+//     phase therefore needs NO per-variable offset table -- its addresses are region base + 4*j' -- and the
+//     bank of every access of a lane is j' mod 32: a group of lanes whose j' are distinct mod 32 is
+//     conflict-free in all of its loads and stores (the plan builder forms the per-layer variable groups
+//     that way).  The check phase reaches an edge's S_j' and c2v word through one packed 32-bit table entry
+//     (two 16-bit byte offsets);
 //   * v2c is never stored: v2c_e = fl64(fl64(prior + S_j) - c2v_e) is rebuilt from S_j and c2v_e, which is
 //     exactly what decoders.py:173,:177 computes (prior = binary32-rounded L during the very first layer
 //     step, decoders.py:148-149, L afterwards);
 //   * check phase: LPC = 1, 2, 4 or 8 lanes share one check (chosen per layer so that the layer fills the
-//     warp: 16-check layers use 2 lanes x 4 edges, single-check layers 8 lanes x 1 edge); each lane scans its
-//     slots for (min1, first argmin, min2, sign parity) and the partial results are merged with xor-shuffles;
-//   * variable phase: lane <-> variable adjacent to the layer, re-summing ALL its c2v in ascending check
-//     order in binary32 (decoders.py:172) through a padded table of shared-memory offsets (padding entries
-//     point at a slot that always holds +0.0f, and s + 0.0f == s).  Layers need not be column-disjoint
+//     warp); min / second min are taken on the ROUNDED per-edge values in binary32 (see ms_check_phase);
+//   * variable phase: lane <-> two variables adjacent to the layer per trip, re-summing ALL their c2v in
+//     ascending check order in binary32 (decoders.py:172).  Layers need not be column-disjoint
 //     (simulator.py:230-234 hands the decoder the partition of the OTHER matrix), so the two phases are
 //     separated by a warp barrier;
 //   * hard decision: fl64(L + S_j) < 0  <=>  S_j < Tf with Tf = L negated and rounded UP to binary32 (the
@@ -35,28 +42,58 @@
 namespace qldpc {
 
 constexpr int kMsMaxWarps = 24;   // 768 threads per CTA -> up to 85 registers per thread
+constexpr int kMsMaxDv = 16;
+constexpr uint32_t kMsPad = 0xFFFFFFFFu;   // padding entry of the check table (short rows)
 
-struct MsSmemLayout {
-    // per-shot state, offsets in bytes from the warp's base
-    int off_c2v;   // float [dc*ms + 4]  (ms = padded slot stride; entry dc*ms is the always-zero slot)
-    int off_S;     // float [n + 1] (entry n: dummy variable of the padded lists)
-    int off_par;   // uint32 [mw]
-    int off_syn;   // uint32 [mw]
-    int bytes;     // multiple of 16
+// Device view of the min-sum tables.  One uint16 blob per plan, copied to shared memory once per CTA; offsets are
+// in uint16 units (32-bit tables start on even offsets).  j' = renumbered variable (descending column weight).
+struct MsTables {
+    int m, n, E;
+    int dc;              // instantiated row weight (>= max row weight)
+    int dv;              // max column weight
+    int nl;              // layers
+    int mw, nw;          // words(m), words(n)
+    int ms;              // row stride of chk (>= m; ms = 4 mod 8 keeps the lane groups of a split check on disjoint banks)
+    int n_pad;           // n rounded up to a multiple of 64 (first-step sweep: two variables per lane and trip)
+    int c2v_words;       // words of the per-shot c2v array (multiple of 32: every region starts on bank 0)
+    int off_chk;         // u32 [dc*ms]   lo16 = 4*j' (byte offset of S_j'), hi16 = byte offset of the edge's c2v word; kMsPad past a short row
+    int off_layer;       // u16 [nl][8]   16-byte record per layer: {qb, qe (range in layer_chk), lanes per check (1, 2, 4 or 8),
+                         //               vb, ve (range in lvar, 32-bit entries, multiples of 32), 0, 0, 0}
+    int off_layer_chk;   // u16 [...]     check indices, layer by layer
+    int off_lvar;        // u32 [...]     lo16 = 4*j'_a, hi16 = 4*j'_b: the two variables of (trip, lane); dummy = 4*n
+    int off_col_ptr;     // u16 [n+2]     CSC pointers in the renumbering (variable n: empty)
+    int off_col_chk;     // u16 [E]       checks of j', ascending
+    int off_rowpar;      // u32 [mw]      parity of the row weights as bit words
+    int off_unperm;      // u16 [32*nw]   4*j' of original variable j (4*n past the end)
+    int len;             // blob length in uint16 units (multiple of 8)
+    int cnt4[kMsMaxDv];  // 4 * number of variables of degree > x
+    int coff4[kMsMaxDv]; // byte offset of region x in the c2v array
 };
 
-__host__ __device__ inline MsSmemLayout ms_layout(const Tables &t)
+struct MsSmemLayout {
+    // per-shot state, offsets in bytes from the warp's base; c2v and S are contiguous (one zero fill)
+    int off_c2v;   // float [c2v_words]
+    int off_S;     // float [n + 1] (entry n: dummy variable of the padded lists) rounded up to 4 words
+    int off_par;   // uint32 [mw]
+    int off_syn;   // uint32 [mw]
+    int zero_words;
+    int bytes;     // multiple of 128: S_j' and every c2v word of j' sit on bank j' mod 32
+};
+
+__host__ __device__ inline MsSmemLayout ms_layout(const MsTables &t)
 {
     MsSmemLayout l;
     int o = 0;
-    l.off_c2v = o; o += 4 * (t.dc * t.ms + 4);
-    o = (o + 15) & ~15;
-    l.off_S = o;   o += 4 * (t.n + 1);
+    l.off_c2v = o; o += 4 * t.c2v_words;
+    l.off_S = o;   o += 4 * ((t.n + 1 + 3) & ~3);
+    l.zero_words = o / 4;
     l.off_par = o; o += 4 * t.mw;
     l.off_syn = o; o += 4 * t.mw;
-    l.bytes = (o + 15) & ~15;
+    l.bytes = (o + 127) & ~127;
     return l;
 }
+
+__host__ __device__ inline int ms_table_bytes(const MsTables &t) { return (t.len * 2 + 127) & ~127; }
 
 // ---- explicit shared-window accessors (addresses are 32-bit shared addresses)
 __device__ __forceinline__ float sld_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
@@ -64,16 +101,14 @@ __device__ __forceinline__ uint32_t sld_u32(uint32_t a) { uint32_t v; asm volati
 __device__ __forceinline__ uint32_t sld_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sst_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sst_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ uint2 sld_v2(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
-__device__ __forceinline__ uint4 sld_v4(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t satom_xor(uint32_t a, uint32_t v) { uint32_t o; asm volatile("atom.shared.xor.b32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o; }
 
 struct MsAddr {          // shared-window byte addresses, warp-uniform
-    uint32_t var_tab;    // uint16 [dc*m]   (CTA tables)
-    uint32_t layer_chk;  // uint16 [...]
+    uint32_t chk;        // u32 [dc*ms]   (CTA tables)
+    uint32_t layer_chk;  // u16 [...]
+    uint32_t col_ptr, col_chk;
     uint32_t c2v, S, par, syn;   // per-warp state
-    uint32_t m2;         // 2*ms : byte stride of one slot row in var_tab
-    uint32_t m4;         // 4*ms : byte stride of one slot row in c2v
+    uint32_t m4;         // 4*ms : byte stride of one slot row in chk
 };
 
 // Check-node phase of one layer with LPC lanes per check (decoders.py:156-169).
@@ -84,10 +119,10 @@ struct MsAddr {          // shared-window byte addresses, warp-uniform
 // with multiplicity): if the minimum of b is attained once, it is attained at the unique argmin of a; if it is attained
 // several times, min2_b == min1_b and every edge receives the same magnitude whichever way a_k == min1 falls.  Edges with
 // a_k != min1 receive g(min1) = min1_b, and b_k != min1_b implies a_k != min1.  Hence the rule "magnitude = (b_k == min1_b ?
-// min2_b : min1_b)" on the ROUNDED per-edge values is bit-identical to the reference, needs no argmin index, and the
-// min / second-min / merge logic becomes binary32 FMNMX instead of binary64 compare+select chains.  The sign of b_k is the
-// sign of v2c_k (v2c is never -0.0: it is a difference of which the minuend is never -0.0, and rounding keeps signs).
-// beta < 0 is handled by the caller passing |beta| and folding the extra sign into `sgn_extra`.
+// min2_b : min1_b)" on the ROUNDED per-edge values is bit-identical to the reference, needs no argmin index (so the order of
+// the edges within a check is free), and the min / second-min / merge logic is binary32 FMNMX instead of binary64
+// compare+select chains.  The sign of b_k is the sign of v2c_k (v2c is never -0.0: it is a difference whose minuend is never
+// -0.0, and rounding keeps signs).  beta < 0: the caller passes |beta| and folds the extra sign into `sgn_extra`.
 template <int DC, bool REGULAR, int LPC>
 __device__ __forceinline__ void ms_check_phase(int qb, int qe, int lane, const MsAddr &A, double prior, double beta, uint32_t sgn_extra)
 {
@@ -101,19 +136,21 @@ __device__ __forceinline__ void ms_check_phase(int qb, int qe, int lane, const M
         const int q = q0 + lane / LPC;
         const bool act = q < qe;
         const uint32_t i = sld_u16(A.layer_chk + 2u * (uint32_t)(act ? q : qb));
-        const uint32_t vt = A.var_tab + (uint32_t)k0 * A.m2 + 2u * i;    // &var_tab[k0*ms + i]
-        const uint32_t cv = A.c2v + (uint32_t)k0 * A.m4 + 4u * i;        // &c2v[k0*ms + i]
+        const uint32_t ct = A.chk + (uint32_t)k0 * A.m4 + 4u * i;        // &chk[k0*ms + i]
         float bs[SPL];                              // signed b_k of the lane's own slots
+        uint32_t ca[SPL];                           // shared address of the slot's c2v word (0 = padding)
         float m1 = inf, m2 = inf;                   // smallest / second smallest |b| (inf if none)
         uint32_t px = 0;                            // xor of the b_k bit patterns: bit 31 = parity of the negative signs
 #pragma unroll
         for (int s = 0; s < SPL; ++s) {
             bs[s] = 0.0f;
+            ca[s] = 0u;
             if (EXACT || k0 + s < DC) {
-                const uint32_t joff = sld_u16(vt + (uint32_t)s * A.m2);       // byte offset of S_j, kPad past a short row
-                if (REGULAR || joff != kPad) {
-                    const double post = __dadd_rn(prior, (double)sld_f32(A.S + joff));                   // :173
-                    const double v = __dsub_rn(post, (double)sld_f32(cv + (uint32_t)s * A.m4));          // :177
+                const uint32_t e = sld_u32(ct + (uint32_t)s * A.m4);
+                if (REGULAR || e != kMsPad) {
+                    ca[s] = A.c2v + (e >> 16);
+                    const double post = __dadd_rn(prior, (double)sld_f32(A.S + (e & 0xffffu)));          // :173
+                    const double v = __dsub_rn(post, (double)sld_f32(ca[s]));                            // :177
                     const float b = __double2float_rn(__dmul_rn(beta, v));                               // :167-168 (f64 product, f32 store)
                     bs[s] = b;
                     px ^= __float_as_uint(b);                                                             // :157-159
@@ -142,9 +179,9 @@ __device__ __forceinline__ void ms_check_phase(int qb, int qe, int lane, const M
 #pragma unroll
             for (int s = 0; s < SPL; ++s) {
                 if (EXACT || k0 + s < DC) {
-                    if (REGULAR || sld_u16(vt + (uint32_t)s * A.m2) != kPad) {
+                    if (REGULAR || ca[s] != 0u) {
                         const uint32_t mag = (fabsf(bs[s]) == m1) ? r2s : r1s;
-                        sst_u32(cv + (uint32_t)s * A.m4, mag ^ (__float_as_uint(bs[s]) & 0x80000000u));
+                        sst_u32(ca[s], mag ^ (__float_as_uint(bs[s]) & 0x80000000u));
                     }
                 }
             }
@@ -152,35 +189,20 @@ __device__ __forceinline__ void ms_check_phase(int qb, int qe, int lane, const M
     }
 }
 
-// DV: number of summed terms per variable (>= max column weight); the offset table has DVS = 4, 8 or 16 entries
-// per variable so that one row is one or two vector loads.
-template <int DV>
-struct VnRow {
-    static constexpr int DVS = DV <= 4 ? 4 : (DV <= 8 ? 8 : 16);
-};
-
-// S_j = sequential binary32 sum of the c2v of variable j in ascending check order (decoders.py:172).  The first term
-// is taken as is (0.0f + c only differs from c for c == -0.0f, and the sign of a zero sum is never observable).
-template <int DV>
-__device__ __forceinline__ float ms_colsum(uint32_t c2v, uint32_t vrow)
+// S_j' = sequential binary32 sum of the c2v of variable j' in ascending check order (decoders.py:172): term x sits at
+// region x + 4*j'.  The first DMIN regions hold every variable (plus a zero word for the dummy variable n).  The others
+// are read unconditionally as well -- for j' >= cnt[x] the address falls into a later region or into S, always inside the
+// warp's own state -- and the value is discarded by a select (cheaper than a predicated load, whose uniform-register
+// operands the compiler guards with votes).  The first term is taken as is (0.0f + c only differs from c for c == -0.0f,
+// and the sign of a zero sum is never observable).
+template <int DV, int DMIN>
+__device__ __forceinline__ float ms_colsum(uint32_t c2vj /* c2v + 4*j' */, uint32_t j4, const MsTables &t)
 {
-    constexpr int DVS = VnRow<DV>::DVS;
-    uint32_t w[DVS / 2];
-    if (DVS == 4) {
-        const uint2 a = sld_v2(vrow);
-        w[0] = a.x; w[1] = a.y;
-    } else {
-#pragma unroll
-        for (int x = 0; x < DVS / 8; ++x) {
-            const uint4 a = sld_v4(vrow + 16u * x);
-            w[4 * x + 0] = a.x; w[4 * x + 1] = a.y; w[4 * x + 2] = a.z; w[4 * x + 3] = a.w;
-        }
-    }
     float term[DV];
 #pragma unroll
     for (int x = 0; x < DV; ++x) {
-        const uint32_t off = (x & 1) ? (w[x >> 1] >> 16) : (w[x >> 1] & 0xffffu);
-        term[x] = sld_f32(c2v + off);
+        term[x] = sld_f32(c2vj + (uint32_t)t.coff4[x]);
+        if (x >= DMIN) term[x] = ((int)j4 < t.cnt4[x]) ? term[x] : 0.0f;
     }
     float s = term[0];
 #pragma unroll
@@ -189,16 +211,16 @@ __device__ __forceinline__ float ms_colsum(uint32_t c2v, uint32_t vrow)
 }
 
 // Cooperative parity update for the variables whose hard decision flipped (rare; one flipped variable per trip).
-__device__ __forceinline__ void ms_apply_flips(uint32_t flips, uint32_t j, int lane, const MsAddr &A, uint32_t col_ptr, uint32_t col_chk, int &delta)
+__device__ __forceinline__ void ms_apply_flips(uint32_t flips, uint32_t j4, int lane, const MsAddr &A, int &delta)
 {
     while (flips) {
         const int src = __ffs(flips) - 1;
         flips &= flips - 1;
-        const uint32_t jf = __shfl_sync(0xffffffffu, j, src);
-        const uint32_t x0 = sld_u16(col_ptr + 2u * jf), x1 = sld_u16(col_ptr + 2u * jf + 2u);
+        const uint32_t jf2 = __shfl_sync(0xffffffffu, j4, src) >> 1;            // 2*j': byte offset into the u16 pointer table
+        const uint32_t x0 = sld_u16(A.col_ptr + jf2), x1 = sld_u16(A.col_ptr + jf2 + 2u);
         const uint32_t x = x0 + lane;
         if (x < x1) {                                                            // lane <-> check of the flipped variable
-            const uint32_t ch = sld_u16(col_chk + 2u * x);
+            const uint32_t ch = sld_u16(A.col_chk + 2u * x);
             const uint32_t bit = 1u << (ch & 31u);
             const uint32_t old = satom_xor(A.par + 4u * (ch >> 5), bit);
             delta += (old & bit) ? -1 : 1;
@@ -207,30 +229,30 @@ __device__ __forceinline__ void ms_apply_flips(uint32_t flips, uint32_t j, int l
 }
 
 // One variable-node pass over TWO variables per lane (two independent load / add chains in flight): new sums, stores,
-// flip detection.  Lists are padded to a multiple of 64 with the dummy variable n.
-template <int DV>
-__device__ __forceinline__ void ms_var_update2(uint32_t ja, uint32_t jb, int lane, const MsAddr &A, uint32_t vn_tab, uint32_t col_ptr,
-                                               uint32_t col_chk, float Tf, int &delta)
+// flip detection.  ja4 / jb4 = 4*j'.
+template <int DV, int DMIN>
+__device__ __forceinline__ void ms_var_update2(uint32_t ja4, uint32_t jb4, int lane, const MsAddr &A, const MsTables &t, float Tf, int &delta)
 {
-    constexpr int DVS = VnRow<DV>::DVS;
-    const uint32_t sa = A.S + 4u * ja, sb = A.S + 4u * jb;
+    const uint32_t sa = A.S + ja4, sb = A.S + jb4;
     const float a_old = sld_f32(sa), b_old = sld_f32(sb);
-    const float a = ms_colsum<DV>(A.c2v, vn_tab + (uint32_t)(2 * DVS) * ja);
-    const float b = ms_colsum<DV>(A.c2v, vn_tab + (uint32_t)(2 * DVS) * jb);
+    const float a = ms_colsum<DV, DMIN>(A.c2v + ja4, ja4, t);
+    const float b = ms_colsum<DV, DMIN>(A.c2v + jb4, jb4, t);
     sst_f32(sa, a);
     sst_f32(sb, b);
     const uint32_t fa = __ballot_sync(0xffffffffu, (a < Tf) != (a_old < Tf));   // hard decision flipped (:173-174)
     const uint32_t fb = __ballot_sync(0xffffffffu, (b < Tf) != (b_old < Tf));
     if (fa | fb) {
-        ms_apply_flips(fa, ja, lane, A, col_ptr, col_chk, delta);
-        ms_apply_flips(fb, jb, lane, A, col_ptr, col_chk, delta);
+        ms_apply_flips(fa, ja4, lane, A, delta);
+        ms_apply_flips(fb, jb4, lane, A, delta);
     }
 }
 
-template <int DC, bool REGULAR, int DV>
-__global__ void __launch_bounds__(kMsMaxWarps * 32, 1) ms_decode_kernel(Tables t, const uint16_t *__restrict__ blob, MsConst c, DecodeIO io)
+// DC: instantiated row weight, REGULAR: every row has exactly DC edges, DV: instantiated column weight, DMIN: number of
+// leading regions that hold every variable (0 = guard all).
+template <int DC, bool REGULAR, int DV, int DMIN>
+__global__ void __launch_bounds__(kMsMaxWarps * 32, 1) ms_decode_kernel(MsTables t, const uint16_t *__restrict__ blob, MsConst c, DecodeIO io)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     {   // graph tables -> shared memory (once per CTA), 16 B per thread per trip
         const uint4 *src = reinterpret_cast<const uint4 *>(blob);
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
@@ -244,24 +266,23 @@ __global__ void __launch_bounds__(kMsMaxWarps * 32, 1) ms_decode_kernel(Tables t
     uint32_t tab;                                                         // shared-window address of the CTA tables
     // opaque to the optimiser on purpose: a plain __cvta_generic_to_shared gets rematerialised (S2UR + ULEA) in every loop
     asm volatile("{ .reg .u64 t64; cvta.to.shared.u64 t64, %1; cvt.u32.u64 %0, t64; }" : "=r"(tab) : "l"(smem));
-    const uint32_t wbase = tab + (uint32_t)((t.len * 2 + 15) & ~15) + (uint32_t)warp * (uint32_t)lay.bytes;
+    const uint32_t wbase = tab + (uint32_t)ms_table_bytes(t) + (uint32_t)warp * (uint32_t)lay.bytes;
     MsAddr A;
-    A.var_tab = tab + 2u * t.off_var;
+    A.chk = tab + 2u * t.off_chk;
     A.layer_chk = tab + 2u * t.off_layer_chk;
+    A.col_ptr = tab + 2u * t.off_col_ptr;
+    A.col_chk = tab + 2u * t.off_col_chk;
     A.c2v = wbase + lay.off_c2v;
     A.S = wbase + lay.off_S;
     A.par = wbase + lay.off_par;
     A.syn = wbase + lay.off_syn;
-    A.m2 = 2u * t.ms;
     A.m4 = 4u * t.ms;
-    const uint32_t col_ptr = tab + 2u * t.off_col_ptr, col_chk = tab + 2u * t.off_col_chk;
-    const uint32_t layer_ptr = tab + 2u * t.off_layer_ptr, layer_lpc = tab + 2u * t.off_layer_lpc;
-    const uint32_t lvar_ptr = tab + 2u * t.off_lvar_ptr, lvar_idx = tab + 2u * t.off_lvar_idx;
-    const uint32_t vn_tab = tab + 2u * t.off_vn, rowpar = tab + 2u * t.off_rowpar;
+    const uint32_t layer_rec = tab + 2u * t.off_layer, lvar = tab + 2u * t.off_lvar;
+    const uint32_t rowpar = tab + 2u * t.off_rowpar, unperm = tab + 2u * t.off_unperm;
     const int n = t.n;
+    const uint32_t n4 = 4u * (uint32_t)n;
     const float Tf = c.Tf;
     const bool init_bit = 0.0f < Tf;                    // decision of a variable whose sum is still 0 (only if L < 0)
-    const int c2v_words = t.dc * t.ms + 4;
 
     for (;;) {
         long long shot = 0;
@@ -270,9 +291,8 @@ __global__ void __launch_bounds__(kMsMaxWarps * 32, 1) ms_decode_kernel(Tables t
         if (shot >= io.shots) break;
 
         // ---- initial state: c2v = 0 (decoders.py:150), S = 0, residual = syndrome (+ H.1 if the all-zero sums decide 1)
-        for (int i = lane * 4; i < c2v_words; i += 128)
+        for (int i = lane * 4; i < lay.zero_words; i += 128)
             asm volatile("st.shared.v4.f32 [%0], {%1,%1,%1,%1};" :: "r"(A.c2v + 4u * i), "f"(0.0f) : "memory");
-        for (int i = lane; i <= n; i += 32) sst_f32(A.S + 4u * i, 0.0f);
         int unsat = 0;
         for (int i = lane; i < t.mw; i += 32) {
             const uint32_t w = io.syn[shot * t.mw + i];
@@ -290,12 +310,12 @@ __global__ void __launch_bounds__(kMsMaxWarps * 32, 1) ms_decode_kernel(Tables t
             // ---------------- first layer step: prior is the binary32-rounded L (decoders.py:148-149) and the variable
             // phase visits EVERY variable (the reference recomputes all posteriors; a variable outside layer 0 has
             // posterior L, which may be negative for p > 1/2)
-            const int qb = sld_u16(layer_ptr), qe = sld_u16(layer_ptr + 2u);
+            const int qb = sld_u16(layer_rec), qe = sld_u16(layer_rec + 2u);
             ms_check_phase<DC, REGULAR, 1>(qb, qe, lane, A, c.Lf, c.abeta, c.sgn);
             __syncwarp();
             int delta = 0;
             for (int q = lane; q < t.n_pad; q += 64)
-                ms_var_update2<DV>((uint32_t)(q < n ? q : n), (uint32_t)(q + 32 < n ? q + 32 : n), lane, A, vn_tab, col_ptr, col_chk, Tf, delta);
+                ms_var_update2<DV, DMIN>(q < n ? 4u * q : n4, q + 32 < n ? 4u * (q + 32) : n4, lane, A, t, Tf, delta);
             unsat += __reduce_add_sync(full, delta);
             __syncwarp();
             converged = unsat == 0;
@@ -303,19 +323,22 @@ __global__ void __launch_bounds__(kMsMaxWarps * 32, 1) ms_decode_kernel(Tables t
         for (; it < c.max_iter && !converged; ++it) {
             for (int l = (it == 0 ? 1 : 0); l < t.nl; ++l) {
                 // ---------------- check-node phase (decoders.py:156-169)
-                const int qb = sld_u16(layer_ptr + 2u * l), qe = sld_u16(layer_ptr + 2u * l + 2u);
-                const int lpc = sld_u16(layer_lpc + 2u * l);
+                uint32_t r0, r1, r2, r3;                                       // the layer's 16-byte record
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(layer_rec + 16u * l));
+                const int qb = r0 & 0xffffu, qe = r0 >> 16, lpc = r1 & 0xffffu;
                 if (lpc == 1) ms_check_phase<DC, REGULAR, 1>(qb, qe, lane, A, c.L, c.abeta, c.sgn);
                 else if (lpc == 2) ms_check_phase<DC, REGULAR, 2>(qb, qe, lane, A, c.L, c.abeta, c.sgn);
                 else if (lpc == 4) ms_check_phase<DC, REGULAR, 4>(qb, qe, lane, A, c.L, c.abeta, c.sgn);
                 else ms_check_phase<DC, REGULAR, 8>(qb, qe, lane, A, c.L, c.abeta, c.sgn);
                 __syncwarp();
                 // ---------------- variable-node phase (decoders.py:172-174) on the variables whose sums changed.  Every
-                // lane runs the same number of trips (lists are padded to a multiple of 64 with the dummy variable n).
-                const int vb = sld_u16(lvar_ptr + 2u * l), ve = sld_u16(lvar_ptr + 2u * l + 2u);
+                // lane runs the same number of trips (lists are padded to whole trips with the dummy variable n).
+                const int vb = r1 >> 16, ve = r2 & 0xffffu;
                 int delta = 0;
-                for (int q = vb + lane; q < ve; q += 64)
-                    ms_var_update2<DV>(sld_u16(lvar_idx + 2u * q), sld_u16(lvar_idx + 2u * q + 64u), lane, A, vn_tab, col_ptr, col_chk, Tf, delta);
+                for (int q = vb + lane; q < ve; q += 32) {
+                    const uint32_t e = sld_u32(lvar + 4u * q);
+                    ms_var_update2<DV, DMIN>(e & 0xffffu, e >> 16, lane, A, t, Tf, delta);
+                }
                 unsat += __reduce_add_sync(full, delta);
                 __syncwarp();
                 // ---------------- H e == syndrome ?  (decoders.py:175-176)
@@ -325,10 +348,10 @@ __global__ void __launch_bounds__(kMsMaxWarps * 32, 1) ms_decode_kernel(Tables t
         // iterations: it+1 of decoders.py:176 on a converging break (the outer ++it has already run; a convergence in the
         // very first step leaves it == 0), else max_iter (:182)
         const int iters = (converged && it == 0) ? 1 : it;
-        // ---- outputs: e_j = (S_j < Tf)
+        // ---- outputs: e_j = (S_j' < Tf)
         for (int w = 0; w < t.nw; ++w) {
             const int j = w * 32 + lane;
-            const uint32_t bits = __ballot_sync(full, j < n && c.max_iter > 0 && sld_f32(A.S + 4u * (uint32_t)(j < n ? j : n)) < Tf);
+            const uint32_t bits = __ballot_sync(full, j < n && c.max_iter > 0 && sld_f32(A.S + sld_u16(unperm + 2u * j)) < Tf);
             if (lane == 0) io.ehat[shot * t.nw + w] = bits;
         }
         if (lane == 0) {
@@ -337,7 +360,7 @@ __global__ void __launch_bounds__(kMsMaxWarps * 32, 1) ms_decode_kernel(Tables t
         }
         if (io.llr) {
             double *dst = io.llr + shot * (long long)n;
-            for (int j = lane; j < n; j += 32) dst[j] = __dadd_rn(c.L, (double)sld_f32(A.S + 4u * j));
+            for (int j = lane; j < n; j += 32) dst[j] = __dadd_rn(c.L, (double)sld_f32(A.S + sld_u16(unperm + 2u * j)));
         }
         if (!converged && io.fail_count) {
             int slot = 0;
@@ -346,7 +369,7 @@ __global__ void __launch_bounds__(kMsMaxWarps * 32, 1) ms_decode_kernel(Tables t
             if (slot < io.fail_cap) {
                 if (lane == 0) io.fail_shot[slot] = (int)shot;
                 double *dst = io.fail_llr + (long long)slot * n;
-                for (int j = lane; j < n; j += 32) dst[j] = __dadd_rn(c.L, (double)sld_f32(A.S + 4u * j));
+                for (int j = lane; j < n; j += 32) dst[j] = __dadd_rn(c.L, (double)sld_f32(A.S + sld_u16(unperm + 2u * j)));
             }
         }
         __syncwarp();

@@ -1,0 +1,297 @@
+// ms_plan.h -- host-side layout planner of the min-sum kernel (no CUDA in this file; also compiled by the CPU unit test
+// tests/test_ms_plan.py through csrc/ms_plan_test.cpp).
+//
+// Decides, for one (Tanner graph, layer list):
+//   * the variable renumbering j -> j' (descending column weight; inside a weight class the order of 16-variable units is
+//     searched so that every layer touches the two halves of the 32 shared-memory banks evenly),
+//   * the region layout of the variable-major c2v array (see ms_kernel.cuh),
+//   * which edge of a check goes to which (lane, step) cell of the check phase,
+//   * the per-layer variable groups of the variable phase (two 32-variable sub-groups per trip),
+// and evaluates the resulting number of shared-memory wavefronts per iteration (every access of a lane to S_j' or to a c2v
+// word falls on bank j' mod 32 because the region bases are multiples of 32 words).
+#pragma once
+#include <stdint.h>
+
+#include <algorithm>
+#include <vector>
+
+namespace qldpc {
+
+struct MsGraphView {
+    int m, n, E;
+    const int *row_ptr, *col_idx;     // CSR, ascending variable per check
+    const int *col_ptr, *row_idx;     // CSC, ascending check per variable
+    int nl;
+    const int *layer_ptr, *layer_chk;
+};
+
+struct MsPlanLayout {
+    int dc_inst = 0, dv = 0, dv_inst = 0, dmin = 0;
+    std::vector<int> order, perm;          // order[j'] = j, perm[j] = j'
+    std::vector<int> edge_rank;            // [E] CSR edge -> rank of its check among the checks of its variable
+    int cnt[16] = {0}, coff[16] = {0};     // variables of degree > x; word offset of region x
+    int c2v_words = 0;
+    std::vector<int> lpc;                  // [nl] lanes per check
+    std::vector<int> slot_edge;            // [m][dc_inst] CSR edge in slot k of check i, -1 = padding
+    std::vector<int> lvar_ptr;             // [nl+1] in packed entries (32 per trip)
+    std::vector<uint32_t> lvar;            // packed (4*j'_a) | (4*j'_b << 16); dummy = 4*n
+    long long wavefronts = 0, ideal = 0;   // per full iteration over all layers (check phase: S load + c2v load + c2v store;
+                                           // variable phase: S load + S store + dv_inst c2v loads per sub-group)
+    int search_evals = 0;
+};
+
+namespace msplan {
+
+inline int lanes_per_check(int layer_checks, int dc_inst)
+{
+    const int lc = std::max(1, layer_checks);
+    int lpc = 1;
+    while (lpc < 8 && lpc * 2 * lc <= 32 && lpc * 2 <= std::max(1, dc_inst)) lpc *= 2;
+    return lpc;
+}
+
+inline int max_mult(const int *bank_cnt)
+{
+    int mx = 0;
+    for (int b = 0; b < 32; ++b) mx = std::max(mx, bank_cnt[b]);
+    return mx;
+}
+
+// Cells of the check phase: slot k of a check is handled by lane group h = k / SPL at step s = k % SPL.  All lanes of a
+// pass (CPP = 32 / LPC checks) execute step s together, so the accesses of one step are {cell (h, s) of every check of the
+// pass}.  Strategy 0 keeps the edges in ascending variable order.  Strategy 1 gives the cell of "virtual lane"
+// v = h * CPP + (check's position in the pass) the edge whose j' has bit 4 equal to bit 4 of v, as far as the check has such
+// edges: for 16-variable circulant blocks this places the two half-warps on different halves of the banks.
+struct Evaluator {
+    const MsGraphView &g;
+    MsPlanLayout &L;
+    std::vector<int> tmp_slot;     // [dc_inst] scratch
+
+    Evaluator(const MsGraphView &g_, MsPlanLayout &L_) : g(g_), L(L_), tmp_slot(64) {}
+
+    void assign_check(int i, int pos_in_pass, int lpc, int strategy, int *slots /*[dc_inst]*/) const
+    {
+        const int dc = L.dc_inst, spl = (dc + lpc - 1) / lpc, cpp = 32 / lpc;
+        const int a = g.row_ptr[i], b = g.row_ptr[i + 1];
+        for (int k = 0; k < dc; ++k) slots[k] = -1;
+        if (strategy == 0) {
+            for (int x = a; x < b; ++x) slots[x - a] = x;
+            return;
+        }
+        int pool[2][32], np[2] = {0, 0}, take[2] = {0, 0};
+        for (int x = a; x < b; ++x) {
+            const int par = (L.perm[g.col_idx[x]] >> 4) & 1;
+            pool[par][np[par]++] = x;
+        }
+        int left = b - a;
+        for (int k = 0; k < dc && left > 0; ++k) {
+            const int h = k / spl;
+            const int want = ((h * cpp + pos_in_pass) >> 4) & 1;
+            int par = want;
+            if (take[par] >= np[par]) par ^= 1;
+            // keep enough cells for the remaining edges: never skip a cell while edges remain
+            slots[k] = pool[par][take[par]++];
+            --left;
+        }
+    }
+
+    // wavefronts of the check phase of layer l with the given strategy; optionally stores the slot assignment
+    long long check_cost(int l, int strategy, bool store, long long *ideal) const
+    {
+        const int dc = L.dc_inst, lpc = L.lpc[l], spl = (dc + lpc - 1) / lpc, cpp = 32 / lpc;
+        const int qb = g.layer_ptr[l], qe = g.layer_ptr[l + 1];
+        long long cost = 0;
+        std::vector<int> slots((size_t)cpp * dc);
+        for (int q0 = qb; q0 < qe; q0 += cpp) {
+            const int nq = std::min(cpp, qe - q0);
+            for (int q = 0; q < nq; ++q) {
+                const int i = g.layer_chk[q0 + q];
+                assign_check(i, q, lpc, strategy, &slots[(size_t)q * dc]);
+                if (store) for (int k = 0; k < dc; ++k) L.slot_edge[(size_t)i * dc + k] = slots[(size_t)q * dc + k];
+            }
+            for (int s = 0; s < spl; ++s) {
+                int bank[32] = {0}, any = 0;
+                for (int q = 0; q < nq; ++q)
+                    for (int h = 0; h < lpc; ++h) {
+                        const int k = h * spl + s;
+                        if (k >= dc) continue;
+                        const int e = slots[(size_t)q * dc + k];
+                        if (e < 0) continue;
+                        bank[L.perm[g.col_idx[e]] & 31]++;
+                        any = 1;
+                    }
+                cost += 3ll * max_mult(bank);
+                if (ideal) *ideal += 3ll * any;
+            }
+        }
+        return cost;
+    }
+
+    // variable groups of layer l: the variables of each residue class (j' mod 32) are dealt to the sub-groups holding the
+    // fewest of that class
+    long long var_cost(int l, bool store, long long *ideal) const
+    {
+        std::vector<int> vs;
+        for (int q = g.layer_ptr[l]; q < g.layer_ptr[l + 1]; ++q) {
+            const int i = g.layer_chk[q];
+            for (int x = g.row_ptr[i]; x < g.row_ptr[i + 1]; ++x) vs.push_back(L.perm[g.col_idx[x]]);
+        }
+        std::sort(vs.begin(), vs.end());
+        vs.erase(std::unique(vs.begin(), vs.end()), vs.end());
+        const int V = (int)vs.size(), G = 2 * ((V + 63) / 64);
+        std::vector<std::vector<int>> sub(G);
+        std::vector<int> res_cnt((size_t)G * 32, 0);
+        std::vector<std::vector<int>> by_res(32);
+        for (int jp : vs) by_res[jp & 31].push_back(jp);
+        // Sub-groups are filled one after the other.  Each takes one variable of every residue class that still has some
+        // (largest classes first), which is conflict-free; only when the sub-groups behind it could not hold the rest does
+        // it take second, third ... members of the largest classes.  Unavoidable conflicts thus end up concentrated in few
+        // sub-groups instead of being spread over all of them.
+        int remaining = V;
+        for (int g2 = 0; g2 < G; ++g2) {
+            const int need = std::min(32, std::max(0, remaining - 32 * (G - g2 - 1)));
+            int taken = 0;
+            for (int round = 0; round < 32 && (round == 0 || taken < need); ++round) {
+                int rs[32];
+                for (int r = 0; r < 32; ++r) rs[r] = r;
+                std::stable_sort(rs, rs + 32, [&](int a2, int b2) { return by_res[a2].size() > by_res[b2].size(); });
+                for (int ri = 0; ri < 32 && taken < 32; ++ri) {
+                    const int r = rs[ri];
+                    if (by_res[r].empty() || (round > 0 && taken >= need)) continue;
+                    sub[g2].push_back(by_res[r].back());
+                    by_res[r].pop_back();
+                    res_cnt[(size_t)g2 * 32 + r]++;
+                    ++taken;
+                }
+            }
+            remaining -= taken;
+        }
+        long long cost = 0;
+        const int per = 2 + L.dv_inst;
+        for (int g2 = 0; g2 < G; ++g2) {
+            int mx = 0;
+            for (int r = 0; r < 32; ++r) mx = std::max(mx, res_cnt[(size_t)g2 * 32 + r]);
+            cost += (long long)per * std::max(mx, 1);
+            if (ideal) *ideal += per;
+        }
+        if (store) {
+            for (int g2 = 0; g2 < G; g2 += 2) {
+                std::sort(sub[g2].begin(), sub[g2].end());
+                std::sort(sub[g2 + 1].begin(), sub[g2 + 1].end());
+                for (int ln = 0; ln < 32; ++ln) {
+                    const uint32_t ja = ln < (int)sub[g2].size() ? (uint32_t)sub[g2][ln] : (uint32_t)g.n;
+                    const uint32_t jb = ln < (int)sub[g2 + 1].size() ? (uint32_t)sub[g2 + 1][ln] : (uint32_t)g.n;
+                    L.lvar.push_back((4u * ja) | ((4u * jb) << 16));
+                }
+            }
+            L.lvar_ptr[l + 1] = (int)L.lvar.size();
+        }
+        return cost;
+    }
+
+    long long total(bool store)
+    {
+        long long cost = 0, ideal = 0;
+        if (store) {
+            L.slot_edge.assign((size_t)g.m * L.dc_inst, -1);
+            L.lvar.clear();
+            L.lvar_ptr.assign(g.nl + 1, 0);
+            // checks outside every layer keep the ascending order (never executed, but the table stays well defined)
+            for (int i = 0; i < g.m; ++i)
+                for (int x = g.row_ptr[i]; x < g.row_ptr[i + 1]; ++x) L.slot_edge[(size_t)i * L.dc_inst + (x - g.row_ptr[i])] = x;
+        }
+        // a check listed in several layers keeps the assignment of its LAST layer: process layers in reverse when storing so
+        // that the first layer wins
+        for (int l = g.nl - 1; l >= 0; --l) {
+            long long id0 = 0;
+            const long long c0 = check_cost(l, 0, false, &id0), c1 = check_cost(l, 1, false, nullptr);
+            const int strat = c1 < c0 ? 1 : 0;
+            cost += std::min(c0, c1);
+            ideal += id0;
+            if (store) check_cost(l, strat, true, nullptr);
+        }
+        for (int l = 0; l < g.nl; ++l) cost += var_cost(l, store, &ideal);
+        if (store) { L.wavefronts = cost; L.ideal = ideal; }
+        return cost;
+    }
+};
+
+}  // namespace msplan
+
+// dc_inst / dv_inst / dmin are the shape of the kernel instance (see qldpc_api.cu: ms_select); `search` enables the unit
+// order search (bounded number of evaluations).
+inline void ms_plan_layout(const MsGraphView &g, int dc_inst, int dv_inst, int dmin, bool search, MsPlanLayout &L)
+{
+    const int n = g.n;
+    L.dc_inst = dc_inst; L.dv_inst = dv_inst; L.dmin = dmin;
+    std::vector<int> deg(n);
+    int dv = 0;
+    for (int j = 0; j < n; ++j) { deg[j] = g.col_ptr[j + 1] - g.col_ptr[j]; dv = std::max(dv, deg[j]); }
+    L.dv = dv;
+    L.order.resize(n);
+    for (int j = 0; j < n; ++j) L.order[j] = j;
+    std::stable_sort(L.order.begin(), L.order.end(), [&](int a, int b) { return deg[a] > deg[b]; });
+    L.perm.resize(n);
+    auto set_perm = [&]() { for (int jp = 0; jp < n; ++jp) L.perm[L.order[jp]] = jp; };
+    set_perm();
+    // regions: multiples of 32 words so that bank(c2v word of j') == bank(S_j') == j' mod 32; an unguarded region (x < dmin)
+    // has room for the always-zero word of the dummy variable n
+    int words = 0;
+    for (int x = 0; x < 16; ++x) {
+        L.cnt[x] = 0;
+        if (x < dv) for (int j = 0; j < n; ++j) L.cnt[x] += deg[j] > x;
+        L.coff[x] = words;
+        if (x < dv_inst) words += (L.cnt[x] + (x < dmin ? 1 : 0) + 31) & ~31;
+    }
+    L.c2v_words = words;
+    L.edge_rank.assign(g.E, 0);
+    {
+        std::vector<int> fill(n, 0);
+        for (int i = 0; i < g.m; ++i)
+            for (int x = g.row_ptr[i]; x < g.row_ptr[i + 1]; ++x) L.edge_rank[x] = fill[g.col_idx[x]]++;
+    }
+    L.lpc.resize(g.nl);
+    for (int l = 0; l < g.nl; ++l) L.lpc[l] = msplan::lanes_per_check(g.layer_ptr[l + 1] - g.layer_ptr[l], dc_inst);
+
+    msplan::Evaluator ev(g, L);
+    long long best = ev.total(false);
+    L.search_evals = 1;
+    if (search && n >= 64) {
+        // units = runs of 16 consecutive j' that lie inside one degree class and start on a multiple of 16
+        std::vector<int> unit_start, unit_class;
+        for (int s = 0; s + 16 <= n; s += 16)
+            if (deg[L.order[s]] == deg[L.order[s + 15]]) { unit_start.push_back(s); unit_class.push_back(deg[L.order[s]]); }
+        const int U = (int)unit_start.size();
+        long long ideal = 0;
+        {   // lower bound: every access group conflict-free
+            MsPlanLayout dummy;
+            (void)dummy;
+            for (int l = 0; l < g.nl; ++l) { long long id = 0; ev.check_cost(l, 0, false, &id); ideal += id; ev.var_cost(l, false, &ideal); }
+        }
+        const int max_evals = 400;
+        bool improved = true;
+        for (int sweep = 0; sweep < 4 && improved && best > ideal && U <= 48; ++sweep) {
+            improved = false;
+            for (int u = 0; u < U && best > ideal; ++u)
+                for (int v = u + 1; v < U && best > ideal; ++v) {
+                    if (unit_class[u] != unit_class[v]) continue;
+                    if (((unit_start[u] ^ unit_start[v]) & 16) == 0) continue;     // same bank half: the swap changes nothing mod 32
+                    if (L.search_evals >= max_evals) goto done;
+                    std::swap_ranges(L.order.begin() + unit_start[u], L.order.begin() + unit_start[u] + 16, L.order.begin() + unit_start[v]);
+                    set_perm();
+                    const long long c = ev.total(false);
+                    ++L.search_evals;
+                    if (c < best) { best = c; improved = true; }
+                    else {
+                        std::swap_ranges(L.order.begin() + unit_start[u], L.order.begin() + unit_start[u] + 16, L.order.begin() + unit_start[v]);
+                        set_perm();
+                    }
+                }
+        }
+    }
+done:
+    set_perm();
+    ev.total(true);
+}
+
+}  // namespace qldpc

@@ -1,0 +1,29 @@
+// ms_plan_test.cpp -- C wrapper around the host-side min-sum layout planner (ms_plan.h) for the CPU unit test
+// tests/test_ms_plan.py (built with g++ by the test; not part of libqldpc_b200.so).
+#include "ms_plan.h"
+
+#include <cstring>
+
+extern "C" int ms_plan_probe(int m, int n, int E, const int *row_ptr, const int *col_idx, int nl, const int *layer_ptr,
+                             const int *layer_chk, int dc_inst, int dv_inst, int dmin, int search,
+                             int *perm_out /*[n]*/, int *slot_edge_out /*[m*dc_inst]*/, int *lvar_ptr_out /*[nl+1]*/,
+                             unsigned *lvar_out, int lvar_cap, long long *stats /*[6]: wavefronts, ideal, evals, c2v_words, lvar_len, baseline*/)
+{
+    std::vector<int> cw(n, 0), col_ptr(n + 1, 0), row_idx(E), fill(n, 0);
+    for (int x = 0; x < E; ++x) cw[col_idx[x]]++;
+    for (int j = 0; j < n; ++j) col_ptr[j + 1] = col_ptr[j] + cw[j];
+    for (int i = 0; i < m; ++i)
+        for (int x = row_ptr[i]; x < row_ptr[i + 1]; ++x) row_idx[col_ptr[col_idx[x]] + fill[col_idx[x]]++] = i;
+    qldpc::MsGraphView g{m, n, E, row_ptr, col_idx, col_ptr.data(), row_idx.data(), nl, layer_ptr, layer_chk};
+    qldpc::MsPlanLayout base, L;
+    qldpc::ms_plan_layout(g, dc_inst, dv_inst, dmin, false, base);
+    qldpc::ms_plan_layout(g, dc_inst, dv_inst, dmin, search != 0, L);
+    std::memcpy(perm_out, L.perm.data(), sizeof(int) * n);
+    std::memcpy(slot_edge_out, L.slot_edge.data(), sizeof(int) * (size_t)m * dc_inst);
+    std::memcpy(lvar_ptr_out, L.lvar_ptr.data(), sizeof(int) * (nl + 1));
+    if ((int)L.lvar.size() > lvar_cap) return -1;
+    std::memcpy(lvar_out, L.lvar.data(), sizeof(unsigned) * L.lvar.size());
+    stats[0] = L.wavefronts; stats[1] = L.ideal; stats[2] = L.search_evals; stats[3] = L.c2v_words; stats[4] = (long long)L.lvar.size();
+    stats[5] = base.wavefronts;
+    return 0;
+}

@@ -11,6 +11,7 @@
 #include "hard_kernels.cuh"
 #include "ms_kernel.cuh"
 #include "ms_lane_kernel.cuh"
+#include "ms_plan.h"
 #include "osd_kernel.cuh"
 #include "sampler_kernel.cuh"
 
@@ -62,42 +63,50 @@ GraphDev graph_dev(const qldpc_plan *p)
     return g;
 }
 
-// ---- min-sum kernel dispatch on (max row weight, regular rows, max column weight)
-typedef void (*ms_kernel_t)(Tables, const uint16_t *, MsConst, DecodeIO);
+// ---- min-sum kernel dispatch on (row weight, regular rows, column weight, unguarded regions)
+typedef void (*ms_kernel_t)(MsTables, const uint16_t *, MsConst, DecodeIO);
 
-template <int DC, int DV>
+template <int DC, int DV, int DMIN>
 ms_kernel_t ms_pick(bool regular)
 {
-    return regular ? (ms_kernel_t)ms_decode_kernel<DC, true, DV> : (ms_kernel_t)ms_decode_kernel<DC, false, DV>;
+    return regular ? (ms_kernel_t)ms_decode_kernel<DC, true, DV, DMIN> : (ms_kernel_t)ms_decode_kernel<DC, false, DV, DMIN>;
 }
 
+// DMIN is either 0 (every region guarded by the degree test) or the fast value of the shape: 3 for column weights <= 5
+// (the lifted-product / Tanner codes have column weights 3..5), DV for the others (column-regular codes such as bicycle).
+constexpr int ms_fast_dmin(int dv_inst) { return dv_inst <= 5 ? 3 : (dv_inst <= 9 ? dv_inst : 0); }
+
 template <int DC>
-ms_kernel_t ms_pick_dv(int dv_inst, bool regular)
+ms_kernel_t ms_pick_dv(int dv_inst, bool fast, bool regular)
 {
     switch (dv_inst) {
-    case 4: return ms_pick<DC, 4>(regular);
-    case 5: return ms_pick<DC, 5>(regular);
-    case 9: return ms_pick<DC, 9>(regular);
-    case 16: return ms_pick<DC, 16>(regular);
+    case 4: return fast ? ms_pick<DC, 4, ms_fast_dmin(4)>(regular) : ms_pick<DC, 4, 0>(regular);
+    case 5: return fast ? ms_pick<DC, 5, ms_fast_dmin(5)>(regular) : ms_pick<DC, 5, 0>(regular);
+    case 9: return fast ? ms_pick<DC, 9, ms_fast_dmin(9)>(regular) : ms_pick<DC, 9, 0>(regular);
+    case 16: return ms_pick<DC, 16, 0>(regular);
     }
     return nullptr;
 }
 
-// Instantiated shapes: row weight <= 4 / 8 / 18 / 32, column weight <= 4 / 5 / 9 / 16.
-ms_kernel_t ms_select(int dc, int dv, bool regular, int *dc_inst, int *dv_inst)
+// Instantiated shapes: row weight <= 4 / 8 / 18 / 32, column weight <= 4 / 5 / 9 / 16.  `full_regions` = number of leading
+// regions that hold every variable; *dmin receives the DMIN of the chosen kernel.
+ms_kernel_t ms_select(int dc, int dv, bool regular, int full_regions, int *dc_inst, int *dv_inst, int *dmin)
 {
     static const int dcs[] = {4, 8, 18, 32}, dvs[] = {4, 5, 9, 16};
     int pc = 0, pv = 0;
     for (int s : dcs) if (!pc && s >= dc) pc = s;
     for (int s : dvs) if (!pv && s >= dv) pv = s;
-    *dc_inst = pc; *dv_inst = pv;
+    *dc_inst = pc; *dv_inst = pv; *dmin = 0;
     if (!pc || !pv) return nullptr;
     const bool reg = regular && pc == dc;
+    const int fd = ms_fast_dmin(pv);
+    const bool fast = fd > 0 && full_regions >= fd;
+    *dmin = fast ? fd : 0;
     switch (pc) {
-    case 4: return ms_pick_dv<4>(pv, reg);
-    case 8: return ms_pick_dv<8>(pv, reg);
-    case 18: return ms_pick_dv<18>(pv, reg);
-    case 32: return ms_pick_dv<32>(pv, reg);
+    case 4: return ms_pick_dv<4>(pv, fast, reg);
+    case 8: return ms_pick_dv<8>(pv, fast, reg);
+    case 18: return ms_pick_dv<18>(pv, fast, reg);
+    case 32: return ms_pick_dv<32>(pv, fast, reg);
     }
     return nullptr;
 }
@@ -116,6 +125,7 @@ struct Geometry {
 typedef void (*ms_lane_kernel_t)(LaneTables, const uint16_t *, MsConst, DecodeIO, LaneScratch);
 struct PlanKernels {
     ms_kernel_t ms = nullptr;
+    MsTables ms_tab{};
     ms_lane_kernel_t ms_lane = nullptr;
     LaneTables lane_tab{};
     bp_kernel_t bp = nullptr;
@@ -249,95 +259,139 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
     if (iterative) {
         if ((long long)dc * m > 65535 || n >= 65535 || p->layer_ptr[nl] > 65535 || dc > 32)
             return bail(QLDPC_ETOOBIG, "code too large for the on-chip decoder tables (need m*row_weight <= 65535, n < 65535, row weight <= 32)");
-        // blob
+        const bool is_ms = o->dec_type == QLDPC_MS;
         std::vector<uint16_t> &b = p->h_blob;
         auto put = [&](int count) { int off = (int)b.size(); b.resize(b.size() + count, 0); return off; };
-        const bool is_ms = o->dec_type == QLDPC_MS;
-        int ms = m;
-        int dc_inst = 0, dv_inst = 0;
-        if (is_ms) {
-            pk->ms = ms_select(dc, dv, regular, &dc_inst, &dv_inst);
-            if (!pk->ms) return bail(QLDPC_ETOOBIG, "min-sum kernels are instantiated for row weight <= 32 and column weight <= 16");
-            dc = dc_inst;              // slot-major tables are padded to the instantiated row weight
-            t.dc = dc;
-            // slot stride: with LPC lanes per check, lane h starts at slot h*SPL, i.e. SPL*ms words further; ms = 4 (mod 8)
-            // puts the two halves of the common 2-lane split 16 banks apart (m = 240 would put them on the same banks)
-            while (ms % 8 != 4) ++ms;
-            if ((long long)dc * ms * 4 + 4 > 65535 || (long long)n * 4 > 65535)
-                return bail(QLDPC_ETOOBIG, "code too large for the 16-bit shared-memory offset tables (need 4*m*row_weight < 65532, 4*n < 65536)");
-        }
-        t.ms = ms;
-        t.off_var = put(dc * ms);
-        std::fill(b.begin() + t.off_var, b.begin() + t.off_var + dc * ms, kPad);
-        for (int i = 0; i < m; ++i)
-            for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x) b[t.off_var + (x - p->row_ptr[i]) * ms + i] = (uint16_t)(4 * p->col_idx[x]);
-        t.off_col_ptr = put(n + 1);
-        for (int j = 0; j <= n; ++j) b[t.off_col_ptr + j] = (uint16_t)p->col_ptr[j];
-        t.off_col_pos = put(E);
-        t.off_col_chk = put(E);
-        for (int x = 0; x < E; ++x) {
-            b[t.off_col_pos + x] = (uint16_t)(col_slot[x] * ms + p->row_idx[x]);
-            b[t.off_col_chk + x] = (uint16_t)p->row_idx[x];
-        }
-        // min-sum variable-phase table: per variable dvs byte offsets into c2v, padded with the zero slot
-        t.dvs = is_ms ? (dv_inst <= 4 ? 4 : (dv_inst <= 8 ? 8 : 16)) : 0;
-        b.resize((b.size() + 7) & ~size_t(7), 0);              // 16-byte aligned rows
-        t.off_vn = put((n + 1) * t.dvs);
-        t.n_pad = (n + 63) & ~63;
-        if (is_ms)
-            for (int j = 0; j < n; ++j)
-                for (int x = 0; x < t.dvs; ++x) {
-                    const int e = p->col_ptr[j] + x;
-                    b[t.off_vn + j * t.dvs + x] = (uint16_t)(e < p->col_ptr[j + 1] ? 4 * (col_slot[e] * ms + p->row_idx[e]) : 4 * dc * ms);
-                }
-        if (is_ms) for (int x = 0; x < t.dvs; ++x) b[t.off_vn + n * t.dvs + x] = (uint16_t)(4 * dc * ms);   // dummy variable n
-        t.off_rowpar = put(2 * t.mw);
-        for (int i = 0; i < m; ++i)
-            if ((p->row_ptr[i + 1] - p->row_ptr[i]) & 1) b[t.off_rowpar + 2 * (i >> 5) + ((i & 31) >> 4)] |= (uint16_t)(1u << (i & 15));
-        // lanes per check of each layer: the largest power of two (<= 8, <= row weight) that keeps the layer in one warp pass
-        t.off_layer_lpc = put(nl);
-        for (int l = 0; l < nl; ++l) {
-            const int lc = std::max(1, p->layer_ptr[l + 1] - p->layer_ptr[l]);
-            int lpc = 1;
-            while (lpc < 8 && lpc * 2 * lc <= 32 && lpc * 2 <= std::max(1, dc)) lpc *= 2;
-            b[t.off_layer_lpc + l] = (uint16_t)lpc;
-        }
-        t.off_layer_ptr = put(nl + 1);
-        for (int l = 0; l <= nl; ++l) b[t.off_layer_ptr + l] = (uint16_t)p->layer_ptr[l];
-        t.off_layer_chk = put((int)p->layer_chk.size());
-        for (size_t x = 0; x < p->layer_chk.size(); ++x) b[t.off_layer_chk + x] = (uint16_t)p->layer_chk[x];
-        // per-layer sorted distinct variable lists
-        std::vector<int> lvar_ptr(nl + 1, 0);
-        std::vector<uint16_t> lvar;
-        std::vector<char> seen(n, 0);
-        for (int l = 0; l < nl; ++l) {
+        auto put32 = [&](int count) { if (b.size() & 1) b.push_back(0); int off = (int)b.size(); b.resize(b.size() + 2 * (size_t)count, 0); return off; };
+        auto set32 = [&](int off, int idx, uint32_t v) { b[off + 2 * idx] = (uint16_t)(v & 0xffffu); b[off + 2 * idx + 1] = (uint16_t)(v >> 16); };
+        // sorted distinct variables adjacent to the checks of layer l
+        auto layer_vars = [&](int l) {
             std::vector<int> vs;
             for (int q = p->layer_ptr[l]; q < p->layer_ptr[l + 1]; ++q) {
                 const int i = p->layer_chk[q];
-                for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x)
-                    if (!seen[p->col_idx[x]]) { seen[p->col_idx[x]] = 1; vs.push_back(p->col_idx[x]); }
+                for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x) vs.push_back(p->col_idx[x]);
             }
             std::sort(vs.begin(), vs.end());
-            for (int v : vs) { seen[v] = 0; lvar.push_back((uint16_t)v); }
-            while (lvar.size() % 64) lvar.push_back((uint16_t)n);   // dummy variable n: uniform trip count per lane
-            lvar_ptr[l + 1] = (int)lvar.size();
-        }
-        if (lvar.size() > 65535) return bail(QLDPC_ETOOBIG, "per-layer variable lists exceed 65535 entries");
-        t.off_lvar_ptr = put(nl + 1);
-        for (int l = 0; l <= nl; ++l) b[t.off_lvar_ptr + l] = (uint16_t)lvar_ptr[l];
-        t.off_lvar_idx = put((int)lvar.size());
-        std::copy(lvar.begin(), lvar.end(), b.begin() + t.off_lvar_idx);
-        b.resize((b.size() + 7) & ~size_t(7), 0);
-        t.len = (int)b.size();
-        if ((rc = upload(&p->d_blob, b))) { qldpc_plan_destroy(p); return rc; }
-
-        const size_t blob_bytes = ((size_t)t.len * 2 + 15) & ~size_t(15);
+            vs.erase(std::unique(vs.begin(), vs.end()), vs.end());
+            return vs;
+        };
         size_t state = 0;
         const void *fn = nullptr;
         if (is_ms) {
-            state = ms_layout(t).bytes;
+            // ================= min-sum tables (layout described in ms_kernel.cuh, planned by ms_plan.h) =================
+            MsTables &mt = pk->ms_tab;
+            if (dv > kMsMaxDv) return bail(QLDPC_ETOOBIG, "min-sum kernels are instantiated for row weight <= 32 and column weight <= 16");
+            int full_regions = 0;      // leading regions that hold every variable: x < min column weight
+            {
+                int dmin_true = n ? *std::min_element(cw.begin(), cw.end()) : 0;
+                full_regions = std::min(dmin_true, dv);
+            }
+            int dc_inst = 0, dv_inst = 0, dmin = 0;
+            pk->ms = ms_select(dc, dv, regular, full_regions, &dc_inst, &dv_inst, &dmin);
+            if (!pk->ms) return bail(QLDPC_ETOOBIG, "min-sum kernels are instantiated for row weight <= 32 and column weight <= 16");
+            MsGraphView gv{m, n, E, p->row_ptr.data(), p->col_idx.data(), p->col_ptr.data(), p->row_idx.data(), nl, p->layer_ptr.data(), p->layer_chk.data()};
+            MsPlanLayout pl;
+            ms_plan_layout(gv, dc_inst, dv_inst, dmin, /*search=*/true, pl);
+            p->plan_wavefronts = pl.wavefronts; p->plan_wavefronts_ideal = pl.ideal;
+            mt.m = m; mt.n = n; mt.E = E; mt.dc = dc_inst; mt.dv = dv; mt.nl = nl; mt.mw = t.mw; mt.nw = t.nw;
+            mt.n_pad = (n + 63) & ~63;
+            for (int x = 0; x < kMsMaxDv; ++x) { mt.cnt4[x] = 4 * pl.cnt[x]; mt.coff4[x] = 4 * pl.coff[x]; }
+            mt.c2v_words = pl.c2v_words;
+            if (4ll * mt.c2v_words > 65535 || 4ll * (n + 1) > 65535)
+                return bail(QLDPC_ETOOBIG, "code too large for the 16-bit shared-memory offset tables (need 4*edges < 65536, 4*n < 65536)");
+            // slot stride: with LPC lanes per check, lane h starts at slot h*SPL, i.e. SPL*ms words further; ms = 4 (mod 8)
+            // puts the lane groups of a split check on disjoint banks
+            int ms = m;
+            while (ms % 8 != 4) ++ms;
+            mt.ms = ms;
+            mt.off_chk = put32(dc_inst * ms);
+            for (int x = 0; x < dc_inst * ms; ++x) set32(mt.off_chk, x, kMsPad);
+            for (int i = 0; i < m; ++i)
+                for (int k = 0; k < dc_inst; ++k) {
+                    const int e = pl.slot_edge[(size_t)i * dc_inst + k];
+                    if (e < 0) continue;
+                    const int jp = pl.perm[p->col_idx[e]];
+                    set32(mt.off_chk, k * ms + i, (uint32_t)(4 * jp) | ((uint32_t)(mt.coff4[pl.edge_rank[e]] + 4 * jp) << 16));
+                }
+            if (pl.lvar.size() > 65535) return bail(QLDPC_ETOOBIG, "per-layer variable lists exceed 65535 entries");
+            b.resize((b.size() + 7) & ~size_t(7), 0);              // 16-byte aligned records
+            mt.off_layer = put(8 * nl);
+            for (int l = 0; l < nl; ++l) {
+                uint16_t *r = &b[mt.off_layer + 8 * l];
+                r[0] = (uint16_t)p->layer_ptr[l]; r[1] = (uint16_t)p->layer_ptr[l + 1]; r[2] = (uint16_t)pl.lpc[l];
+                r[3] = (uint16_t)pl.lvar_ptr[l]; r[4] = (uint16_t)pl.lvar_ptr[l + 1];
+            }
+            mt.off_layer_chk = put((int)p->layer_chk.size());
+            for (size_t x = 0; x < p->layer_chk.size(); ++x) b[mt.off_layer_chk + x] = (uint16_t)p->layer_chk[x];
+            mt.off_lvar = put32((int)pl.lvar.size());
+            for (size_t x = 0; x < pl.lvar.size(); ++x) set32(mt.off_lvar, (int)x, pl.lvar[x]);
+            // CSC in the renumbering (flip handling)
+            mt.off_col_ptr = put(n + 2);
+            mt.off_col_chk = put(E);
+            {
+                int pos = 0;
+                for (int jp = 0; jp < n; ++jp) {
+                    b[mt.off_col_ptr + jp] = (uint16_t)pos;
+                    const int j = pl.order[jp];
+                    for (int x = p->col_ptr[j]; x < p->col_ptr[j + 1]; ++x) b[mt.off_col_chk + pos++] = (uint16_t)p->row_idx[x];
+                }
+                b[mt.off_col_ptr + n] = (uint16_t)pos;
+                b[mt.off_col_ptr + n + 1] = (uint16_t)pos;
+            }
+            mt.off_rowpar = put32(t.mw);
+            {
+                std::vector<uint32_t> rp(t.mw, 0u);
+                for (int i = 0; i < m; ++i) if ((p->row_ptr[i + 1] - p->row_ptr[i]) & 1) rp[i >> 5] |= 1u << (i & 31);
+                for (int w2 = 0; w2 < t.mw; ++w2) set32(mt.off_rowpar, w2, rp[w2]);
+            }
+            mt.off_unperm = put(32 * t.nw);
+            for (int j = 0; j < 32 * t.nw; ++j) b[mt.off_unperm + j] = (uint16_t)(4 * (j < n ? pl.perm[j] : n));
+            b.resize((b.size() + 7) & ~size_t(7), 0);
+            mt.len = (int)b.size();
+            t.len = mt.len;
+            state = ms_layout(mt).bytes;
             fn = (const void *)pk->ms;
         } else {
+            // ================= sum-product tables (slot-major edge layout, see common.cuh) =================
+            const int ms = m;
+            t.ms = ms;
+            t.off_var = put(dc * ms);
+            std::fill(b.begin() + t.off_var, b.begin() + t.off_var + dc * ms, kPad);
+            for (int i = 0; i < m; ++i)
+                for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x) b[t.off_var + (x - p->row_ptr[i]) * ms + i] = (uint16_t)(4 * p->col_idx[x]);
+            t.off_col_ptr = put(n + 1);
+            for (int j = 0; j <= n; ++j) b[t.off_col_ptr + j] = (uint16_t)p->col_ptr[j];
+            t.off_col_pos = put(E);
+            t.off_col_chk = put(E);
+            for (int x = 0; x < E; ++x) {
+                b[t.off_col_pos + x] = (uint16_t)(col_slot[x] * ms + p->row_idx[x]);
+                b[t.off_col_chk + x] = (uint16_t)p->row_idx[x];
+            }
+            t.dvs = 0;
+            t.off_vn = 0;
+            t.n_pad = (n + 31) & ~31;
+            t.off_rowpar = put(2 * t.mw);
+            for (int i = 0; i < m; ++i)
+                if ((p->row_ptr[i + 1] - p->row_ptr[i]) & 1) b[t.off_rowpar + 2 * (i >> 5) + ((i & 31) >> 4)] |= (uint16_t)(1u << (i & 15));
+            t.off_layer_lpc = put(nl);
+            t.off_layer_ptr = put(nl + 1);
+            for (int l = 0; l <= nl; ++l) b[t.off_layer_ptr + l] = (uint16_t)p->layer_ptr[l];
+            t.off_layer_chk = put((int)p->layer_chk.size());
+            for (size_t x = 0; x < p->layer_chk.size(); ++x) b[t.off_layer_chk + x] = (uint16_t)p->layer_chk[x];
+            std::vector<int> lvar_ptr(nl + 1, 0);
+            std::vector<uint16_t> lvar;
+            for (int l = 0; l < nl; ++l) {
+                for (int v : layer_vars(l)) lvar.push_back((uint16_t)v);
+                while (lvar.size() % 32) lvar.push_back((uint16_t)n);   // dummy variable n: uniform trip count per lane
+                lvar_ptr[l + 1] = (int)lvar.size();
+            }
+            if (lvar.size() > 65535) return bail(QLDPC_ETOOBIG, "per-layer variable lists exceed 65535 entries");
+            t.off_lvar_ptr = put(nl + 1);
+            for (int l = 0; l <= nl; ++l) b[t.off_lvar_ptr + l] = (uint16_t)lvar_ptr[l];
+            t.off_lvar_idx = put((int)lvar.size());
+            std::copy(lvar.begin(), lvar.end(), b.begin() + t.off_lvar_idx);
+            b.resize((b.size() + 7) & ~size_t(7), 0);
+            t.len = (int)b.size();
             state = bp_layout(t).bytes;
             // lanes per check = smallest power of two >= row weight (one lane per edge)
             if (dc <= 4) pk->bp = bp_decode_kernel<4>;
@@ -346,6 +400,8 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             else pk->bp = bp_decode_kernel<32>;
             fn = (const void *)pk->bp;
         }
+        if ((rc = upload(&p->d_blob, b))) { qldpc_plan_destroy(p); return rc; }
+        const size_t blob_bytes = is_ms ? (size_t)ms_table_bytes(pk->ms_tab) : (((size_t)t.len * 2 + 15) & ~size_t(15));
         if (!fn) return bail(QLDPC_ETOOBIG, "row weight not supported");
         if (blob_bytes + state > (size_t)kMaxSmemPerCta)
             return bail(QLDPC_ETOOBIG, "decoder state of one shot does not fit in 227 KB of shared memory");
@@ -476,6 +532,9 @@ int64_t qldpc_plan_info(const qldpc_plan *p, int what)
     case 9: return p->tab.dv;
     case 10: return p->rank_h;
     case 11: return p->use_lane ? 1 : 0;
+    case 12: return p->plan_wavefronts;
+    case 13: return p->plan_wavefronts_ideal;
+    case 14: return (int64_t)p->state_bytes;
     }
     return -1;
 }
@@ -519,7 +578,7 @@ static int launch_decode(qldpc_plan *p, const uint32_t *syn, int64_t shots, uint
             sc.eb = (uint32_t *)(sb + b_c2v + b_S + b_par);
             pk->ms_lane<<<lgrid, 256, p->lane_smem, st>>>(lt, p->d_lane_blob, c, io, sc);
         } else {
-            kernels_of(p)->ms<<<grid, p->threads, p->smem_bytes, st>>>(p->tab, p->d_blob, c, io);
+            kernels_of(p)->ms<<<grid, p->threads, p->smem_bytes, st>>>(kernels_of(p)->ms_tab, p->d_blob, c, io);
         }
         break;
     }

@@ -104,6 +104,24 @@ def test_ms_other_beta_and_max_iter_edge(cuda_device):
         assert np.array_equal(got["e_hat"], want["e_hat"]) and np.array_equal(got["iters"], want["iters"])
 
 
+@pytest.mark.parametrize("beta", [-0.75, 1.0 / 3.0, 0.1, 1.7, 0.0])
+def test_ms_rounded_minimum_rule(beta, cuda_device):
+    """The kernel takes min / second min on the binary32-ROUNDED magnitudes (see ms_check_phase); the reference takes them
+    in binary64 before rounding.  Many iterations at a high error rate make the messages diverge until distinct binary64
+    magnitudes round to the same binary32 value -- the case in which the two formulations could differ if the argument in
+    the kernel header were wrong -- and non-dyadic or negative normalisations exercise the rounding of the product."""
+    from qldpcsim_b200 import pcmlibrary
+    from qldpcsim_b200.pcm import layerize
+    Hx, Hz = [(h % 2).astype(np.int8) for h in pcmlibrary.by_name("LP04_0")]
+    rng = np.random.default_rng(11)
+    e = (rng.random((1500, Hz.shape[1])) < 0.09).astype(np.int64)
+    syn = ((e @ Hz.T.astype(np.int64)) % 2).astype(np.uint8)
+    want, got = _cmp(Hz, syn, "MS", cuda_device, p=0.03, max_iter=40, layers=layerize(Hx), beta=beta)
+    assert (want["iters"] == 40).sum() > 50, "the case must contain non-converging shots"
+    assert np.array_equal(got["e_hat"], want["e_hat"]) and np.array_equal(got["iters"], want["iters"])
+    assert np.array_equal(got["converged"], want["converged"])
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_bp_bf_ng_random_irregular(seed, cuda_device):
     rng = np.random.default_rng(50 + seed)
