@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define QLDPC_ABI_VERSION 1
+#define QLDPC_ABI_VERSION 2
 
 enum { QLDPC_OK = 0, QLDPC_EINVAL = -1, QLDPC_ECUDA = -2, QLDPC_ETOOBIG = -3, QLDPC_ENOMEM = -4 };
 
@@ -42,8 +42,13 @@ enum {
     QLDPC_CNT_ITERS_X = 4,  /* sum of nIterX      simulator.py:291 */
     QLDPC_CNT_ITERS_Z = 5,  /* sum of nIterZ      simulator.py:292 */
     QLDPC_CNT_SHOTS  = 6,
-    QLDPC_CNT_RESERVED = 7,
-    QLDPC_NUM_COUNTERS = 8
+    /* Extension: the four outcome classes of README.md:15-22, which the reference's own
+     * counters do not implement (its "degenerate" test is vacuous, simulator.py:296-298).  Filled only when both
+     * plans carry logical operators (qldpc_plan_set_logicals); shots = exact + true_degen + logical + fail_any. */
+    QLDPC_CNT_TRUE_DEGEN = 7, /* both syndromes reproduced, residual is a stabiliser, not an exact match   */
+    QLDPC_CNT_LOGICAL = 8,    /* both syndromes reproduced, residual acts on the logical qubits            */
+    QLDPC_CNT_FAIL_ANY = 9,   /* at least one of the two syndromes not reproduced ("decoder failure")      */
+    QLDPC_NUM_COUNTERS = 10
 };
 
 /* Tanner graph + check schedule, host memory, as produced by the PCM compiler (qldpcsim_b200/pcm.py).
@@ -84,7 +89,7 @@ int qldpc_plan_destroy(qldpc_plan *plan);
  * 6 dynamic shared memory bytes per CTA, 7 shots resident per CTA, 8 max row weight, 9 max column weight,
  * 10 GF(2) rank of H (gf2math.rank, gf2math.py:91-135), 11 whether the lane-per-shot min-sum kernel is used,
  * 12 / 13 shared-memory wavefronts per iteration modelled by the min-sum layout planner / its conflict-free bound,
- * 14 bytes of shared-memory state per shot. */
+ * 14 bytes of shared-memory state per shot, 15 number of attached logical operators. */
 int64_t qldpc_plan_info(const qldpc_plan *plan, int what);
 
 /* Decode `shots` syndromes.  Replaces the per-shot calls NG_decoder / BF_decoder / MS_decoder / BP_decoder
@@ -125,6 +130,13 @@ int qldpc_classify(const qldpc_plan *plan_x, const qldpc_plan *plan_z,
                    const uint32_t *syn_z_bits, const uint32_t *syn_x_bits,
                    const int32_t *iters_x, const int32_t *iters_z,
                    int64_t shots, int64_t *counters, void *stream);
+
+/* Attach a basis of logical operators to a plan (extension; no counterpart in the reference,
+ * whose README.md:15-22 defines the classes but whose simulator.py:296-298 cannot tell them apart).
+ *   logical_rows host [k][words(n)] bit-packed.  For the plan built from Hz (X-error decode) pass a basis of the logical
+ *   Z operators -- ker(Hx) modulo rowspace(Hz); for the plan built from Hx pass the logical X operators.  With both
+ *   attached, qldpc_classify also fills QLDPC_CNT_TRUE_DEGEN / _LOGICAL (it always fills _FAIL_ANY).  k = 0 detaches. */
+int qldpc_plan_set_logicals(qldpc_plan *plan, const uint32_t *logical_rows, int32_t k);
 
 /* On-device depolarizing sampler + syndrome generator: the stand-in for Stim's sampler
  * (simulator.py:43-160, :196-197).  Qubit q of global shot s draws u from a counter-based generator keyed by

@@ -245,3 +245,27 @@ def simulate_p(Hx: np.ndarray, Hz: np.ndarray, record: np.ndarray, p: float, dec
         res["_details"] = {"eX": eX, "eZ": eZ, "itX": dx["iters"], "itZ": dz["iters"], "convX": dx["converged"],
                            "convZ": dz["converged"], "exact": exact, "failX": failX, "failZ": failZ}
     return res
+
+
+def outcome_classes(Hx: np.ndarray, Hz: np.ndarray, errX, errZ, eX, eZ) -> dict:
+    """The four outcome classes of the reference's README.md:15-22 (its code does not implement them: simulator.py:296-298
+    is vacuous).  Checker for the library's extension counters; deliberately a DIFFERENT method from the library's
+    (which tests the residual against logical operators): here a residual with matching syndromes is a stabiliser iff
+    appending it to the stabiliser matrix does not raise the GF(2) rank (gf2math.rank semantics, gf2math.py:91-135)."""
+    Hx = (np.asarray(Hx) % 2).astype(np.uint8)
+    Hz = (np.asarray(Hz) % 2).astype(np.uint8)
+    dX = (np.asarray(errX).astype(np.uint8) ^ np.asarray(eX).astype(np.uint8)) & 1
+    dZ = (np.asarray(errZ).astype(np.uint8) ^ np.asarray(eZ).astype(np.uint8)) & 1
+    rx, rz = gf2_rank(Hx), gf2_rank(Hz)
+    out = {"exact": 0, "degenerate": 0, "logical_error": 0, "decoder_failure": 0}
+    fail = ((dX.astype(np.int64) @ Hz.T.astype(np.int64)) % 2).any(axis=1) | ((dZ.astype(np.int64) @ Hx.T.astype(np.int64)) % 2).any(axis=1)
+    for s in range(dX.shape[0]):
+        if fail[s]:
+            out["decoder_failure"] += 1
+        elif not dX[s].any() and not dZ[s].any():
+            out["exact"] += 1
+        else:
+            in_x = (not dX[s].any()) or gf2_rank(np.vstack([Hx, dX[s:s + 1]])) == rx      # X residual in rowspace(Hx)
+            in_z = (not dZ[s].any()) or gf2_rank(np.vstack([Hz, dZ[s:s + 1]])) == rz
+            out["degenerate" if (in_x and in_z) else "logical_error"] += 1
+    return out

@@ -13,13 +13,15 @@ LIB_PATH = os.path.join(HERE, "libqldpc_b200.so")
 
 NG, BF, MS, BP = 0, 1, 2, 3
 DEC_TYPES = {"NG": NG, "BF": BF, "MS": MS, "BP": BP}
-NUM_COUNTERS = 8
+NUM_COUNTERS = 10
 CNT_FAIL_X, CNT_FAIL_Z, CNT_EXACT, CNT_DEGEN, CNT_ITERS_X, CNT_ITERS_Z, CNT_SHOTS = range(7)
+CNT_TRUE_DEGEN, CNT_LOGICAL, CNT_FAIL_ANY = 7, 8, 9      # README.md:15-22 classes (extension, see include/qldpc_b200.h)
+ABI_VERSION = 2
 
 # every symbol include/qldpc_b200.h declares
 EXPORTS = ["qldpc_abi_version", "qldpc_last_error", "qldpc_words", "qldpc_plan_create", "qldpc_plan_destroy",
            "qldpc_plan_info", "qldpc_decode", "qldpc_decode_host", "qldpc_osd", "qldpc_classify", "qldpc_sample",
-           "qldpc_launch_count"]
+           "qldpc_launch_count", "qldpc_plan_set_logicals"]
 
 
 class Graph(ctypes.Structure):
@@ -62,7 +64,8 @@ def lib():
     L.qldpc_classify.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp]
     L.qldpc_sample.argtypes = [vp, vp, f64, u64, i64, i64, vp, vp, vp, vp, vp]
     L.qldpc_launch_count.restype = i64
-    if L.qldpc_abi_version() != 1:
+    L.qldpc_plan_set_logicals.argtypes = [vp, vp, i32]
+    if L.qldpc_abi_version() != ABI_VERSION:
         raise QldpcError("libqldpc_b200.so ABI version mismatch; rebuild")
     _lib = L
     return L

@@ -89,6 +89,8 @@ struct qldpc_plan {
     int32_t *d_row_ptr = nullptr, *d_col_idx = nullptr, *d_col_ptr = nullptr, *d_row_idx = nullptr;
     uint32_t *d_hbits = nullptr;   // [m][nw] bit-packed rows of H (OSD, sampler, classification)
     uint32_t *d_hcol = nullptr;    // [n][mw] bit-packed columns of H (syndrome of a sparse vector)
+    uint32_t *d_lcol = nullptr;    // [n][lkw] bit-packed columns of the attached logical-operator basis (or null)
+    int logical_k = 0, lkw = 0;
     unsigned long long *d_work = nullptr;
     int *d_fail_count = nullptr;
     int sm_count = 0;

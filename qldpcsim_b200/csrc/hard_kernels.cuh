@@ -150,6 +150,8 @@ struct ClassifyArgs {
     GraphDev gz, gx;                       // gz = Hz (X-error decode), gx = Hx (Z-error decode)
     const uint32_t *colmask_z, *colmask_x; // [nw] OR of the rows of Hz / Hx
     const uint32_t *hcol_z, *hcol_x;       // [n][mw] bit-packed columns of Hz / Hx
+    const uint32_t *lcol_z, *lcol_x;       // [n][kw] bit-packed columns of the logical-Z / logical-X bases, or null
+    int kwz, kwx;                          // words(k) of the two bases
     const uint32_t *errx, *errz, *ehx, *ehz, *synz, *synx;
     const int32_t *itx, *itz;
     long long shots;
@@ -180,6 +182,29 @@ __device__ __forceinline__ bool syndrome_mismatch(const GraphDev &g, const uint3
     return __any_sync(0xffffffffu, acc != 0u);
 }
 
+// L d (mod 2) != 0 for d = x ^ y (two bit-packed vectors in global memory), by XOR-ing the bit-packed COLUMNS of L selected
+// by the set bits of d, one word of the result per lane.  lcol: [n][kw] words, kw <= 32.
+__device__ __forceinline__ bool anticommutes_with_logical(const uint32_t *__restrict__ lcol, int kw, int nw, const uint32_t *x,
+                                                          const uint32_t *y, int lane)
+{
+    uint32_t acc = 0u;
+    for (int w0 = 0; w0 < nw; w0 += 32) {
+        const uint32_t word_l = (w0 + lane < nw) ? (x[w0 + lane] ^ y[w0 + lane]) : 0u;
+        uint32_t nz = __ballot_sync(0xffffffffu, word_l != 0u);
+        while (nz) {
+            const int wl = __ffs(nz) - 1;
+            nz &= nz - 1;
+            uint32_t bits = __shfl_sync(0xffffffffu, word_l, wl);
+            while (bits) {
+                const int j = (w0 + wl) * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                if (lane < kw) acc ^= lcol[(size_t)j * kw + lane];
+            }
+        }
+    }
+    return __any_sync(0xffffffffu, acc != 0u);
+}
+
 __global__ void __launch_bounds__(256) classify_kernel(ClassifyArgs a)
 {
     __shared__ unsigned long long cta_cnt[QLDPC_NUM_COUNTERS];
@@ -189,7 +214,8 @@ __global__ void __launch_bounds__(256) classify_kernel(ClassifyArgs a)
     const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int nw = a.gz.nw;
-    unsigned long long c_fx = 0, c_fz = 0, c_ex = 0, c_dg = 0, c_ix = 0, c_iz = 0, c_sh = 0;
+    unsigned long long c_fx = 0, c_fz = 0, c_ex = 0, c_dg = 0, c_ix = 0, c_iz = 0, c_sh = 0, c_td = 0, c_lg = 0, c_fa = 0;
+    const bool have_logicals = a.lcol_z != nullptr && a.lcol_x != nullptr;
     for (long long s = warp_global; s < a.shots; s += nwarps) {
         const uint32_t *ex = a.errx + s * nw, *ez = a.errz + s * nw, *hx = a.ehx + s * nw, *hz = a.ehz + s * nw;
         bool diff = false, touch = false;
@@ -202,7 +228,15 @@ __global__ void __launch_bounds__(256) classify_kernel(ClassifyArgs a)
         const bool degen = !exact && !__any_sync(0xffffffffu, touch);
         const bool fx = syndrome_mismatch(a.gz, a.hcol_z, hx, a.synz + s * a.gz.mw, lane);
         const bool fz = syndrome_mismatch(a.gx, a.hcol_x, hz, a.synx + s * a.gx.mw, lane);
+        // README classes (README.md:15-22): the residual of a shot whose two syndromes are reproduced lies in the normaliser;
+        // it is a stabiliser iff its X part commutes with every logical Z and its Z part with every logical X
+        bool logical = false;
+        if (have_logicals && !exact && !fx && !fz)                                   // warp-uniform
+            logical = anticommutes_with_logical(a.lcol_z, a.kwz, nw, ex, hx, lane) | anticommutes_with_logical(a.lcol_x, a.kwx, nw, ez, hz, lane);
         if (lane == 0) {
+            const bool fail_any = fx | fz;
+            c_fa += fail_any;
+            if (have_logicals && !exact && !fail_any) { c_lg += logical; c_td += !logical; }
             c_fx += fx; c_fz += fz; c_ex += exact; c_dg += degen;
             c_ix += (unsigned long long)a.itx[s]; c_iz += (unsigned long long)a.itz[s]; c_sh += 1;
         }
@@ -215,6 +249,9 @@ __global__ void __launch_bounds__(256) classify_kernel(ClassifyArgs a)
         atomicAdd(&cta_cnt[QLDPC_CNT_ITERS_X], c_ix);
         atomicAdd(&cta_cnt[QLDPC_CNT_ITERS_Z], c_iz);
         atomicAdd(&cta_cnt[QLDPC_CNT_SHOTS], c_sh);
+        atomicAdd(&cta_cnt[QLDPC_CNT_TRUE_DEGEN], c_td);
+        atomicAdd(&cta_cnt[QLDPC_CNT_LOGICAL], c_lg);
+        atomicAdd(&cta_cnt[QLDPC_CNT_FAIL_ANY], c_fa);
     }
     __syncthreads();
     if (threadIdx.x < QLDPC_NUM_COUNTERS && cta_cnt[threadIdx.x]) atomicAdd(&a.counters[threadIdx.x], cta_cnt[threadIdx.x]);

@@ -506,13 +506,33 @@ int qldpc_plan_destroy(qldpc_plan *p)
     if (!p) return QLDPC_OK;
     cudaSetDevice(p->device);
     cudaFree(p->d_blob); cudaFree(p->d_lane_blob); cudaFree(p->d_row_ptr); cudaFree(p->d_col_idx); cudaFree(p->d_col_ptr); cudaFree(p->d_row_idx);
-    cudaFree(p->d_hbits); cudaFree(p->d_hcol); cudaFree(p->d_work); cudaFree(p->d_fail_count);
+    cudaFree(p->d_hbits); cudaFree(p->d_hcol); cudaFree(p->d_lcol); cudaFree(p->d_work); cudaFree(p->d_fail_count);
     for (int s = 0; s < 7; ++s) if (p->scratch[s]) cudaFree(p->scratch[s]);
     delete kernels_of(p);
     for (int s = 0; s < 3; ++s) if (p->streams[s]) cudaStreamDestroy(p->streams[s]);
     for (int e = 0; e < 8; ++e) if (p->events[e]) cudaEventDestroy(p->events[e]);
     for (int s = 0; s < 4; ++s) if (p->pinned[s]) cudaFreeHost(p->pinned[s]);
     delete p;
+    return QLDPC_OK;
+}
+
+int qldpc_plan_set_logicals(qldpc_plan *p, const uint32_t *rows, int32_t k)
+{
+    if (!p || k < 0 || (k > 0 && !rows)) return fail(QLDPC_EINVAL, "null argument");
+    if (k > 1024) return fail(QLDPC_ETOOBIG, "at most 1024 logical operators per plan");
+    CU_TRY(cudaSetDevice(p->device));
+    CU_TRY(cudaDeviceSynchronize());          // a classification using the old basis may still be in flight
+    cudaFree(p->d_lcol);
+    p->d_lcol = nullptr; p->logical_k = 0; p->lkw = 0;
+    if (k == 0) return QLDPC_OK;
+    const int n = p->tab.n, nw = p->tab.nw, kw = (k + 31) / 32;
+    std::vector<uint32_t> cols((size_t)n * kw, 0u);
+    for (int r = 0; r < k; ++r)
+        for (int j = 0; j < n; ++j)
+            if ((rows[(size_t)r * nw + (j >> 5)] >> (j & 31)) & 1u) cols[(size_t)j * kw + (r >> 5)] |= 1u << (r & 31);
+    int rc = upload(&p->d_lcol, cols);
+    if (rc) return rc;
+    p->logical_k = k; p->lkw = kw;
     return QLDPC_OK;
 }
 
@@ -535,6 +555,7 @@ int64_t qldpc_plan_info(const qldpc_plan *p, int what)
     case 12: return p->plan_wavefronts;
     case 13: return p->plan_wavefronts_ideal;
     case 14: return (int64_t)p->state_bytes;
+    case 15: return p->logical_k;
     }
     return -1;
 }
@@ -725,6 +746,9 @@ int qldpc_classify(const qldpc_plan *px, const qldpc_plan *pz, const uint32_t *e
     a.colmask_z = px->d_hbits + (size_t)px->tab.m * px->tab.nw;
     a.colmask_x = pz->d_hbits + (size_t)pz->tab.m * pz->tab.nw;
     a.hcol_z = px->d_hcol; a.hcol_x = pz->d_hcol;
+    const bool lg = px->d_lcol && pz->d_lcol;
+    a.lcol_z = lg ? px->d_lcol : nullptr; a.lcol_x = lg ? pz->d_lcol : nullptr;
+    a.kwz = px->lkw; a.kwx = pz->lkw;
     if (px->tab.mw > 32 || pz->tab.mw > 32) return fail(QLDPC_ETOOBIG, "classification supports up to 1024 checks per matrix");
     a.errx = errx; a.errz = errz; a.ehx = ehx; a.ehz = ehz; a.synz = synz; a.synx = synx; a.itx = itx; a.itz = itz;
     a.shots = shots;

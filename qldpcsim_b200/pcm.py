@@ -7,6 +7,8 @@ PCM compiler (host side): dense parity-check matrix -> what the CUDA library's p
                        decoders.py:224), CSC, degree statistics, quasi-cyclic structure if present.
  * `layerize`        : the check partition of the layered / serial schedules (simulator.py:212-224).
  * `schedule_layers` : (layersX, layersZ) as the driver builds them (simulator.py:228-236).
+ * `logical_operators`: bases of the logical X / Z operators of the CSS code (what the true outcome classes of
+                       README.md:15-22 need; the reference never computes them).
  * `detect_qc`       : recovers (L, base shift matrix) of a circulant-permutation lifted matrix
                        (PCMlibrary.py:129-138, 195-201) so kernels may replace index loads by arithmetic.
 The device-side tables (slot-major edge layout, per-layer variable lists) are derived from the CSR + layers by
@@ -144,3 +146,83 @@ def flatten_layers(layers: Sequence[np.ndarray]) -> Tuple[np.ndarray, np.ndarray
     else:
         idx = np.zeros(0, dtype=np.int32)
     return ptr, np.ascontiguousarray(idx)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# logical operators (extension: the reference's README defines the outcome classes, its code cannot separate them)
+# ---------------------------------------------------------------------------------------------------------
+def _rows_to_ints(M: np.ndarray) -> List[int]:
+    M = (np.asarray(M) % 2).astype(np.uint8)
+    return [int.from_bytes(np.packbits(r, bitorder="little").tobytes(), "little") for r in M]
+
+
+def _ints_to_rows(vals: Sequence[int], n: int) -> np.ndarray:
+    out = np.zeros((len(vals), n), dtype=np.int8)
+    nbytes = (n + 7) // 8
+    for i, v in enumerate(vals):
+        out[i] = np.unpackbits(np.frombuffer(v.to_bytes(nbytes, "little"), dtype=np.uint8), bitorder="little")[:n]
+    return out
+
+
+class _GF2Span:
+    """Incremental row space over GF(2) on Python integers (bit j = column j): reduced basis keyed by leading bit."""
+
+    def __init__(self):
+        self.piv = {}
+
+    def reduce(self, v: int) -> int:
+        while v:
+            h = v.bit_length() - 1
+            b = self.piv.get(h)
+            if b is None:
+                return v
+            v ^= b
+        return 0
+
+    def add(self, v: int) -> bool:
+        v = self.reduce(v)
+        if not v:
+            return False
+        self.piv[v.bit_length() - 1] = v
+        return True
+
+
+def gf2_nullspace(M: np.ndarray) -> List[int]:
+    """Basis of {v : M v = 0 (mod 2)} as integers (same space as gf2math.nullSpace, gf2math.py:12-50; own algorithm:
+    eliminate [M^T | I] and read the identity part of the rows whose M^T part vanished)."""
+    M = (np.asarray(M) % 2).astype(np.uint8)
+    m, n = M.shape
+    cols = _rows_to_ints(M.T)                     # n integers of m bits
+    rows = [(c << n) | (1 << j) for j, c in enumerate(cols)]    # high part: column of M, low part: e_j
+    piv = {}
+    null = []
+    for v in rows:
+        while v >> n:
+            h = v.bit_length() - 1
+            b = piv.get(h)
+            if b is None:
+                piv[h] = v
+                v = 0
+                break
+            v ^= b
+        if v:
+            null.append(v & ((1 << n) - 1))
+    return null
+
+
+def logical_operators(Hx: np.ndarray, Hz: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """(Lx, Lz): k x n bases of the logical X operators ker(Hz)/rowspace(Hx) and the logical Z operators
+    ker(Hx)/rowspace(Hz), k = n - rank(Hx) - rank(Hz).
+
+    A residual X error d with Hz d = 0 is a stabiliser iff Lz d = 0; a residual Z error d with Hx d = 0 iff Lx d = 0."""
+    Hx = (np.asarray(Hx) % 2).astype(np.uint8)
+    Hz = (np.asarray(Hz) % 2).astype(np.uint8)
+    n = Hx.shape[1]
+    out = []
+    for stab, other in ((Hx, Hz), (Hz, Hx)):          # Lx: in ker(Hz), independent of rowspace(Hx); then Lz
+        span = _GF2Span()
+        for v in _rows_to_ints(stab):
+            span.add(v)
+        logical = [v for v in gf2_nullspace(other) if span.add(v)]
+        out.append(_ints_to_rows(logical, n))
+    return out[0], out[1]

@@ -8,7 +8,7 @@ lists; the partition built from Hx (`layersX`) is used for the decode on Hz and 
 never does; NG and BF get neither iterations nor schedule (BF therefore always runs its default 50 iterations).
 
 Shots are independent, so with torch.distributed initialised the shots are sharded over the ranks (one process per
-GPU) and the only collective is one all-reduce(SUM) of the int64[8] outcome counters.
+GPU) and the only collective is one all-reduce(SUM) of the int64[10] outcome counters.
 """
 from __future__ import annotations
 
@@ -19,7 +19,7 @@ import numpy as np
 
 from . import _lib, bitpack, sampler
 from .decoders import Decoder
-from .pcm import load_matrix, schedule_layers  # noqa: F401  (load_matrix re-exported like the reference)
+from .pcm import load_matrix, logical_operators, schedule_layers  # noqa: F401  (load_matrix re-exported like the reference)
 
 DEFAULT_SEED = 0x5EED
 
@@ -43,7 +43,7 @@ def dist_info() -> Tuple[int, int]:
 
 
 def reduce_counters(counters):
-    """all_reduce(SUM) of the int64[8] counter vector over the default process group (NCCL on GPU tensors, gloo on
+    """all_reduce(SUM) of the int64[10] counter vector over the default process group (NCCL on GPU tensors, gloo on
     CPU tensors).  No-op without an initialised process group."""
     _, world = dist_info()
     if world > 1:
@@ -52,17 +52,22 @@ def reduce_counters(counters):
     return counters
 
 
-def counters_to_result(c, shots: int) -> dict:
-    """The dict simulate_p returns (simulator.py:308-315)."""
+def counters_to_result(c, shots: int, classes: bool = False) -> dict:
+    """The dict simulate_p returns (simulator.py:308-315); with `classes` also the four outcome classes of the
+    reference's README.md:15-22, which its own counters cannot separate (extension)."""
     c = [int(x) for x in c]
-    return {
+    extra = {}
+    if classes:
+        extra = {"outcome_exact": c[_lib.CNT_EXACT], "outcome_degenerate": c[_lib.CNT_TRUE_DEGEN],
+                 "outcome_logical_error": c[_lib.CNT_LOGICAL], "outcome_decoder_failure": c[_lib.CNT_FAIL_ANY]}
+    return {**{
         "DecFailures_X": c[_lib.CNT_FAIL_X],
         "DecFailures_Z": c[_lib.CNT_FAIL_Z],
         "decSuccessExact": c[_lib.CNT_EXACT],
         "decSuccessDegen": c[_lib.CNT_DEGEN],
         "Avg_number_of_iterations_X": c[_lib.CNT_ITERS_X] / float(shots),
         "Avg_number_of_iterations_Z": c[_lib.CNT_ITERS_Z] / float(shots),
-    }
+    }, **extra}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -72,7 +77,7 @@ class Pipeline:
     """Device pipeline for one (Hx, Hz, p, decoder configuration): two decode plans + sampler + classifier."""
 
     def __init__(self, Hx, Hz, p: float, decType: str = "MS", decIterations: int = 99, decSchedule: str = "F",
-                 OSDorder: int = -1, device: Optional[int] = None):
+                 OSDorder: int = -1, device: Optional[int] = None, logicals: bool = False):
         Hx = (np.asarray(Hx) % 2).astype(np.int8)
         Hz = (np.asarray(Hz) % 2).astype(np.int8)
         if Hx.shape[1] != Hz.shape[1]:
@@ -97,6 +102,15 @@ class Pipeline:
         import torch
         self.torch = torch
         self.device = torch.device("cuda", self.decX.device)
+        self.logicals = bool(logicals)
+        if logicals:
+            # true outcome classes (README.md:15-22): the X residual is tested against the logical Z operators (attached to
+            # the plan on Hz), the Z residual against the logical X operators (plan on Hx)
+            Lx, Lz = logical_operators(Hx, Hz)
+            for dec, L in ((self.decX, Lz), (self.decZ, Lx)):
+                rows = np.ascontiguousarray(bitpack.pack_rows(L.astype(bool))) if L.shape[0] else np.zeros((0, bitpack.words(self.n)), np.uint32)
+                _lib.check(_lib.lib().qldpc_plan_set_logicals(dec.handle, rows.ctypes.data if rows.size else None, int(L.shape[0])))
+            self.k = int(Lx.shape[0])
 
     # -- inputs -------------------------------------------------------------------------------------------
     def upload_record(self, record: np.ndarray):
@@ -122,7 +136,7 @@ class Pipeline:
 
     # -- one pass -----------------------------------------------------------------------------------------
     def run(self, synz, synx, errx, errz, counters=None, keep: bool = False):
-        """decode X, decode Z, classify.  Returns the int64[8] device counter tensor (accumulated into `counters`)."""
+        """decode X, decode Z, classify.  Returns the int64[10] device counter tensor (accumulated into `counters`)."""
         t = self.torch
         if counters is None:
             counters = t.zeros(_lib.NUM_COUNTERS, dtype=t.int64, device=self.device)
@@ -141,7 +155,7 @@ class Pipeline:
 def simulate_p(Hx: np.ndarray, Hz: np.ndarray, p: float, shots: int = 1000, decType: str = "MS",
                decIterations: int = 99, decSchedule: str = "F", OSDorder: int = -1, rngSeed: Optional[int] = None,
                *, record: Optional[np.ndarray] = None, sampler_kind: str = "host", chunk: int = 1 << 20,
-               device: Optional[int] = None, details: bool = False) -> dict:
+               device: Optional[int] = None, details: bool = False, classes: bool = False) -> dict:
     """Batched equivalent of simulator.py:167-315; returns the same six-key dict.
 
     record       : optional bool array (shots, m_z + m_x + 2n) = [sy_z | sy_x | errX | errZ]; when given it replaces
@@ -150,8 +164,10 @@ def simulate_p(Hx: np.ndarray, Hz: np.ndarray, p: float, shots: int = 1000, decT
                    'device'-- Philox sampler on the GPU keyed by the global shot index (for 10^6+ shots)
     Unlike the reference (whose rngSeed never reaches Stim, simulator.py:187-188) runs are reproducible.
     With torch.distributed initialised each rank processes its shard_range and counters are all-reduced.
+    classes      : also count the four outcome classes of README.md:15-22 (exact / degenerate / logical error / decoder
+                   failure) through the code's logical operators; adds the keys outcome_* to the returned dict.
     """
-    pipe = Pipeline(Hx, Hz, p, decType, decIterations, decSchedule, OSDorder, device)
+    pipe = Pipeline(Hx, Hz, p, decType, decIterations, decSchedule, OSDorder, device, logicals=classes)
     t = pipe.torch
     rank, world = dist_info()
     lo, hi = shard_range(shots, rank, world)
@@ -185,7 +201,7 @@ def simulate_p(Hx: np.ndarray, Hz: np.ndarray, p: float, shots: int = 1000, decT
         raise ValueError("sampler_kind must be 'host' or 'device'")
     reduce_counters(counters)
     t.cuda.synchronize(pipe.device)
-    res = counters_to_result(counters.cpu().numpy(), shots)
+    res = counters_to_result(counters.cpu().numpy(), shots, classes=classes)
     if details:
         res["_details"] = {k: t.cat([d[k] for d in kept]).cpu().numpy() for k in kept[0]} if kept else {}
         res["_counters"] = counters.cpu().numpy()
@@ -201,6 +217,14 @@ def format_results(p, results, shots: int) -> str:
         qbler = 1. - (r['decSuccessExact'] + r['decSuccessDegen']) / shots
         lines.append(f"         {pT:10.2e}         |     {qbler:7.2e}      |       {r['DecFailures_X']:5},{r['DecFailures_Z']:5}       "
                      f"|      {r['Avg_number_of_iterations_X']:5.2f}, {r['Avg_number_of_iterations_Z']:5.2f}")
+    if results and "outcome_exact" in results[0]:
+        lines += ['', '   Outcome classes (README: perfect match / degenerate / logical error / decoder failure)',
+                  '   Depolarizing probability |   exact   | degenerate | logical error | decoder failure | logical+failure rate',
+                  '----------------------------+-----------+------------+---------------+-----------------+----------------------']
+        for pT, r in zip(p, results):
+            bad = (r['outcome_logical_error'] + r['outcome_decoder_failure']) / shots
+            lines.append(f"         {pT:10.2e}         | {r['outcome_exact']:9} | {r['outcome_degenerate']:10} | {r['outcome_logical_error']:13} "
+                         f"| {r['outcome_decoder_failure']:15} |       {bad:7.2e}")
     return "\n".join(lines)
 
 
@@ -231,13 +255,14 @@ def main(argv=None):
                         help="Decoder scheduling method: [F] flooding; [L] layered; [S] serial.")
     parser.add_argument("--OSDorder", type=int, default=-1, help="Ordered Statistics Decoding order.")
     parser.add_argument("--sampler", choices=['host', 'device'], default='host', help="Where shots are drawn.")
+    parser.add_argument("--classes", action="store_true", help="Also count exact / degenerate / logical-error / failure outcomes.")
     args = parser.parse_args(argv)
     print('\n   Command line arguments:')
     print(args)
     print('')
     simulate(HxFile=args.Hx, HzFile=args.Hz, p=args.p, shots=args.shots, decType=args.decType,
              decIterations=args.decIterations, decSchedule=args.decSchedule, OSDorder=args.OSDorder,
-             rngSeed=args.rngSeed, sampler_kind=args.sampler)
+             rngSeed=args.rngSeed, sampler_kind=args.sampler, classes=args.classes)
 
 
 if __name__ == "__main__":

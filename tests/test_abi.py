@@ -18,7 +18,7 @@ def test_header_symbols_exported():
         assert hasattr(L, sym), f"{sym} declared in the header but not exported"
     assert sorted(declared) == sorted(_lib.EXPORTS)
     lib = _lib.lib()
-    assert lib.qldpc_abi_version() == 1
+    assert lib.qldpc_abi_version() == _lib.ABI_VERSION == 2
     assert lib.qldpc_words(1) == 1 and lib.qldpc_words(32) == 1 and lib.qldpc_words(33) == 2 and lib.qldpc_words(544) == 17
     assert lib.qldpc_launch_count() == 0
 

@@ -306,10 +306,40 @@ def test_full_size_properties(cuda_device):
     assert c1[0] == int((~conv).sum().item()) and c1[1] == int((~last["convZ"].bool()).sum().item())
     assert c1[6] == shots and c1[4] == int(it.sum().item())
     # chunking invariance (what multi-GPU sharding relies on)
-    c2 = torch.zeros(8, dtype=torch.int64, device=pipe.device)
+    from qldpcsim_b200 import _lib
+    c2 = torch.zeros(_lib.NUM_COUNTERS, dtype=torch.int64, device=pipe.device)
     for lo in range(0, shots, 300_000):
         hi = min(shots, lo + 300_000)
         pipe.run(synz[lo:hi], synx[lo:hi], errx[lo:hi], errz[lo:hi], counters=c2)
     assert np.array_equal(c1, c2.cpu().numpy())
     # exact matches cannot be failures
     assert c1[2] + max(c1[0], c1[1]) <= shots
+
+
+CLASS_CASES = [("steane", "MS", "F", 0.08, 4000), ("shor", "NG", "F", 0.08, 4000), ("LP04_0", "MS", "L", 0.08, 3000),
+               ("LP04_0", "NG", "F", 0.03, 3000), ("LP118_0", "MS", "L", 0.09, 1500), ("bicycle", "BF", "F", 0.02, 1500)]
+
+
+@pytest.mark.parametrize("code,decType,sched,p,shots", CLASS_CASES)
+def test_outcome_classes(code, decType, sched, p, shots, cuda_device):
+    """Extension counters (README.md:15-22: exact / degenerate / logical error / decoder failure) against an independent
+    CPU restatement (rank test instead of logical operators); the reference-compatible counters are unaffected."""
+    from oracle import oracle
+    from qldpcsim_b200 import bitpack, pcmlibrary, sampler, simulator
+    Hx, Hz = [(h % 2).astype(np.int8) for h in pcmlibrary.by_name(code)]
+    rec = sampler.sample_record(Hx, Hz, p, shots, seed=99)
+    plain = simulator.simulate_p(Hx, Hz, p, shots=shots, decType=decType, decIterations=20, decSchedule=sched, record=rec)
+    got = simulator.simulate_p(Hx, Hz, p, shots=shots, decType=decType, decIterations=20, decSchedule=sched, record=rec,
+                               details=True, classes=True)
+    for k in plain:
+        assert got[k] == plain[k], k
+    n = Hx.shape[1]
+    eX = bitpack.unpack_rows(got["_details"]["eX"].view(np.uint32), n)
+    eZ = bitpack.unpack_rows(got["_details"]["eZ"].view(np.uint32), n)
+    _, _, errX, errZ = oracle.split_record(rec, Hz.shape[0], Hx.shape[0], n)
+    want = oracle.outcome_classes(Hx, Hz, errX, errZ, eX, eZ)
+    assert got["outcome_exact"] == want["exact"] == got["decSuccessExact"]
+    assert got["outcome_degenerate"] == want["degenerate"]
+    assert got["outcome_logical_error"] == want["logical_error"]
+    assert got["outcome_decoder_failure"] == want["decoder_failure"]
+    assert sum(want.values()) == shots
