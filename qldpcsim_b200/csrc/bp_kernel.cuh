@@ -27,6 +27,7 @@ struct BpSmemLayout {
     int off_c2v;   // double [dc*m]
     int off_T;     // double [n + 1]
     int off_par, off_syn;
+    int off_team;  // 16 bytes: shot index mailbox (int64), unsatisfied-check count (int32)
     int bytes;
 };
 
@@ -38,6 +39,8 @@ __host__ __device__ inline BpSmemLayout bp_layout(const Tables &t)
     l.off_T = o;   o += 8 * (t.n + 1);
     l.off_par = o; o += 4 * t.mw;
     l.off_syn = o; o += 4 * t.mw;
+    o = (o + 7) & ~7;
+    l.off_team = o; o += 16;
     l.bytes = (o + 15) & ~15;
     return l;
 }
@@ -72,7 +75,12 @@ __device__ __forceinline__ double bp_colsum(const double *c2v, const uint16_t *c
     return res;
 }
 
-template <int LPC>
+// W warps ("team") share one shot: the binary64 state limits a CTA to ~11 shots (LP118_0), and 11 warps cannot keep the
+// issue slots busy through the long dependent instruction streams of tanh / atanh (measured 49 % issue-active).  The team
+// splits the passes of the check phase and the trips of the variable phase between its warps and meets at a named barrier
+// (bar.sync id, 32*W) between the phases; the unsatisfied-check count lives in shared memory.  Results are bit-identical
+// for any W (every edge and every variable is still computed by exactly one lane, in the same arithmetic order).
+template <int LPC, int W>
 __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint16_t *__restrict__ blob, BpConst c, DecodeIO io)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -97,34 +105,46 @@ __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(full, (int)(threadIdx.x >> 5), 0);
-    unsigned char *base = smem + ((t.len * 2 + 15) & ~15) + (size_t)warp * lay.bytes;
+    const int team = warp / W, sub = warp % W;
+    const int tl = sub * 32 + lane;                            // thread index within the team
+    constexpr int TT = 32 * W;                                 // threads per team
+    unsigned char *base = smem + ((t.len * 2 + 15) & ~15) + (size_t)team * lay.bytes;
     double *c2v = reinterpret_cast<double *>(base + lay.off_c2v);
     double *T = reinterpret_cast<double *>(base + lay.off_T);
     uint32_t *par = reinterpret_cast<uint32_t *>(base + lay.off_par);
     uint32_t *syn = reinterpret_cast<uint32_t *>(base + lay.off_syn);
+    volatile long long *team_shot = reinterpret_cast<volatile long long *>(base + lay.off_team);
+    int *team_unsat = reinterpret_cast<int *>(base + lay.off_team + 8);
     const int m = t.ms, n = t.n, dc = t.dc;   // m: slot stride
     const double one_m_eps = 1.0 - c.eps;                     // `1-eps` of decoders.py:257
     const bool init_bit = c.L0 < 0.0;
     constexpr int CPP = 32 / LPC;
     const int k = lane % LPC;                                  // slot of this lane
     const int grp = lane & ~(LPC - 1);                         // first lane of the check's group
+    auto team_sync = [&]() {
+        if (W == 1) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" :: "r"(team + 1), "r"(TT) : "memory");
+    };
 
     for (;;) {
-        long long shot = 0;
-        if (lane == 0) shot = (long long)atomicAdd(io.work_counter, 1ull);
-        shot = __shfl_sync(full, shot, 0);
+        if (tl == 0) *team_shot = (long long)atomicAdd(io.work_counter, 1ull);
+        team_sync();
+        const long long shot = *team_shot;
         if (shot >= io.shots) break;
-        for (int i = lane; i < dc * m; i += 32) c2v[i] = 0.0;       // :236
-        for (int i = lane; i <= n; i += 32) T[i] = c.L0;            // v2c = L0 (:235)
-        int unsat = 0;
-        for (int i = lane; i < t.mw; i += 32) {
-            const uint32_t w = io.syn[shot * t.mw + i];
-            const uint32_t p0 = init_bit ? (w ^ rowpar[i]) : w;
-            syn[i] = w; par[i] = p0;
-            unsat += __popc(p0);
+        for (int i = tl; i < dc * m; i += TT) c2v[i] = 0.0;         // :236
+        for (int i = tl; i <= n; i += TT) T[i] = c.L0;              // v2c = L0 (:235)
+        if (sub == 0) {
+            int u = 0;
+            for (int i = lane; i < t.mw; i += 32) {
+                const uint32_t w = io.syn[shot * t.mw + i];
+                const uint32_t p0 = init_bit ? (w ^ rowpar[i]) : w;
+                syn[i] = w; par[i] = p0;
+                u += __popc(p0);
+            }
+            u = __reduce_add_sync(full, u);
+            if (lane == 0) *team_unsat = u;
         }
-        unsat = __reduce_add_sync(full, unsat);
-        __syncwarp();
+        team_sync();
 
         bool converged = false, first = true;
         int it = 0;
@@ -132,7 +152,7 @@ __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint
             for (int l = 0; l < t.nl; ++l) {
                 // ---------------- check-node phase (decoders.py:249-262), one lane per edge
                 const int qb = layer_ptr[l], qe = layer_ptr[l + 1];
-                for (int q0 = qb; q0 < qe; q0 += CPP) {
+                for (int q0 = qb + sub * CPP; q0 < qe; q0 += W * CPP) {
                     const int q = q0 + lane / LPC;
                     const bool act = q < qe;
                     const int i = layer_chk[act ? q : qb];
@@ -156,11 +176,11 @@ __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint
                     }
                     __syncwarp();
                 }
-                __syncwarp();
+                team_sync();
                 // ---------------- variable-node phase (decoders.py:265-280) on the variables whose messages changed
                 const int vb = first ? 0 : lvar_ptr[l], ve = first ? t.n_pad : lvar_ptr[l + 1];
                 int delta = 0;
-                for (int q = vb + lane; q < ve; q += 32) {
+                for (int q = vb + tl; q < ve; q += TT) {
                     const int j = first ? (q < n ? q : n) : lvar_idx[q];
                     const int t0 = (j < n) ? col_ptr[j] : 0, cnt = (j < n) ? col_ptr[j + 1] - t0 : 0;
                     const double tot = __dadd_rn(c.L0, bp_colsum(c2v, col_pos, t0, cnt, t.dv));   // :269 / :275
@@ -180,34 +200,42 @@ __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint
                         }
                     }
                 }
-                unsat += __reduce_add_sync(full, delta);
-                __syncwarp();
+                delta = __reduce_add_sync(full, delta);
+                if (lane == 0 && delta != 0) atomicAdd(team_unsat, delta);
+                team_sync();
                 first = false;
-                if (unsat == 0) { converged = true; break; }                           // :283-285
+                // every warp of the team reads the count before any of them can pass the next barrier, and the count is
+                // only modified after that barrier
+                if (*reinterpret_cast<volatile int *>(team_unsat) == 0) { converged = true; break; }   // :283-285
             }
         }
         const int iters = it;   // ++it has run after a converging break: it+1 of :285, else max_iter
-        for (int w = 0; w < t.nw; ++w) {
+        for (int w = sub; w < t.nw; w += W) {
             const int j = w * 32 + lane;
             const uint32_t bits = __ballot_sync(full, j < n && c.max_iter > 0 && T[j < n ? j : n] < 0.0);
             if (lane == 0) io.ehat[shot * t.nw + w] = bits;
         }
-        if (lane == 0) { io.iters[shot] = iters; if (io.conv) io.conv[shot] = converged ? 1 : 0; }
+        if (tl == 0) { io.iters[shot] = iters; if (io.conv) io.conv[shot] = converged ? 1 : 0; }
         if (io.llr) {
             double *dst = io.llr + shot * (long long)n;
-            for (int j = lane; j < n; j += 32) dst[j] = T[j];
+            for (int j = tl; j < n; j += TT) dst[j] = T[j];
         }
         if (!converged && io.fail_count) {
-            int slot = 0;
-            if (lane == 0) slot = atomicAdd(io.fail_count, 1);
-            slot = __shfl_sync(full, slot, 0);
+            if (tl == 0) {
+                const int s2 = atomicAdd(io.fail_count, 1);
+                *team_shot = s2;                           // reuse the mailbox: the shot index has been consumed by every warp
+                if (s2 < io.fail_cap) io.fail_shot[s2] = (int)shot;
+            }
+            // the mailbox write must not overtake the other warps' read of the shot index above: they read it right after the
+            // first barrier of this trip, long before this point, and cannot start the next trip before the barrier below
+            team_sync();
+            const int slot = (int)*team_shot;
             if (slot < io.fail_cap) {
-                if (lane == 0) io.fail_shot[slot] = (int)shot;
                 double *dst = io.fail_llr + (long long)slot * n;
-                for (int j = lane; j < n; j += 32) dst[j] = T[j];
+                for (int j = tl; j < n; j += TT) dst[j] = T[j];
             }
         }
-        __syncwarp();
+        team_sync();
     }
 }
 

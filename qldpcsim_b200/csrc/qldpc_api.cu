@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -129,6 +130,7 @@ struct PlanKernels {
     ms_lane_kernel_t ms_lane = nullptr;
     LaneTables lane_tab{};
     bp_kernel_t bp = nullptr;
+    int bp_team = 1;           // warps per shot of the sum-product kernel
     bool regular = false;
 };
 static PlanKernels *kernels_of(qldpc_plan *p) { return reinterpret_cast<PlanKernels *>(p->scratch[7]); }
@@ -353,8 +355,12 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             fn = (const void *)pk->ms;
         } else {
             // ================= sum-product tables (slot-major edge layout, see common.cuh) =================
+            // slot stride = m: padding it to spread the slots of a check over the banks was measured SLOWER (LP118_0: one
+            // shot fewer per SM, 4.04e10 vs 4.26e10 edge-iterations/s) -- the kernel is bound by the binary64 tanh / atanh
+            // instruction streams and by occupancy, not by shared-memory wavefronts
             const int ms = m;
             t.ms = ms;
+            if ((long long)dc * ms > 65535) return bail(QLDPC_ETOOBIG, "code too large for the on-chip decoder tables (need m*row_weight <= 65535, n < 65535, row weight <= 32)");
             t.off_var = put(dc * ms);
             std::fill(b.begin() + t.off_var, b.begin() + t.off_var + dc * ms, kPad);
             for (int i = 0; i < m; ++i)
@@ -394,10 +400,31 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             t.len = (int)b.size();
             state = bp_layout(t).bytes;
             // lanes per check = smallest power of two >= row weight (one lane per edge)
-            if (dc <= 4) pk->bp = bp_decode_kernel<4>;
-            else if (dc <= 8) pk->bp = bp_decode_kernel<8>;
-            else if (dc <= 16) pk->bp = bp_decode_kernel<16>;
-            else pk->bp = bp_decode_kernel<32>;
+            // warps per shot ("team"): as many as fit 32 warps per CTA, at most 3, and at most 15 teams (named barriers 1..15)
+            {
+                const size_t bb = ((size_t)t.len * 2 + 15) & ~size_t(15);
+                const int teams_fit = (int)std::min<size_t>(32, bb + state <= (size_t)kMaxSmemPerCta ? ((size_t)kMaxSmemPerCta - bb) / state : 0);
+                // a team only pays off when a layer has work for all of its warps
+                int max_layer = 0;
+                for (int l = 0; l < nl; ++l) max_layer = std::max(max_layer, p->layer_ptr[l + 1] - p->layer_ptr[l]);
+                const int lpc = dc <= 4 ? 4 : (dc <= 8 ? 8 : (dc <= 16 ? 16 : 32));
+                const int passes = (max_layer + 32 / lpc - 1) / (32 / lpc);
+                // measured on LP118_0 (11 shots fit): W = 1 / 2 / 3 / 4 -> 4.3 / 7.1 / 7.6 / 8.0e10 edge-iterations/s, i.e. the
+                // total number of resident warps is what counts, not the number of resident shots
+                int W = 1, best_warps = std::min(teams_fit, 32);
+                for (int w2 = 2; w2 <= 4 && w2 <= passes; ++w2) {
+                    const int teams = std::min(teams_fit, std::min(32 / w2, 15));
+                    if (teams * w2 > best_warps) { best_warps = teams * w2; W = w2; }
+                }
+                if (const char *ev = getenv("QLDPC_BP_TEAM")) { const int w2 = atoi(ev); if (w2 >= 1 && w2 <= 4 && teams_fit >= 1) W = w2; }   // tuning knob
+                pk->bp_team = W;
+#define QLDPC_BP_PICK(L) (W == 4 ? (bp_kernel_t)bp_decode_kernel<L, 4> : (W == 3 ? (bp_kernel_t)bp_decode_kernel<L, 3> : (W == 2 ? (bp_kernel_t)bp_decode_kernel<L, 2> : (bp_kernel_t)bp_decode_kernel<L, 1>)))
+                if (dc <= 4) pk->bp = QLDPC_BP_PICK(4);
+                else if (dc <= 8) pk->bp = QLDPC_BP_PICK(8);
+                else if (dc <= 16) pk->bp = QLDPC_BP_PICK(16);
+                else pk->bp = QLDPC_BP_PICK(32);
+#undef QLDPC_BP_PICK
+            }
             fn = (const void *)pk->bp;
         }
         if ((rc = upload(&p->d_blob, b))) { qldpc_plan_destroy(p); return rc; }
@@ -406,8 +433,10 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
         if (blob_bytes + state > (size_t)kMaxSmemPerCta)
             return bail(QLDPC_ETOOBIG, "decoder state of one shot does not fit in 227 KB of shared memory");
         int warps = (int)std::min<size_t>(is_ms ? kMsMaxWarps : 32, ((size_t)kMaxSmemPerCta - blob_bytes) / state);
+        const int team = is_ms ? 1 : pk->bp_team;
+        if (!is_ms) warps = std::min(warps, std::min(32 / team, team > 1 ? 15 : 32));        // shots per CTA (named barriers 1..15)
         p->state_bytes = state;
-        p->threads = warps * kWarp;
+        p->threads = warps * team * kWarp;
         p->shots_per_cta = warps;
         p->smem_bytes = blob_bytes + (size_t)warps * state;
         p->grid = p->sm_count;
