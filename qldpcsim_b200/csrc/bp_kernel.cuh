@@ -83,7 +83,7 @@ __device__ __forceinline__ double bp_colsum(const double *c2v, const uint16_t *c
 template <int LPC, int W>
 __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint16_t *__restrict__ blob, BpConst c, DecodeIO io)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     uint16_t *tab = reinterpret_cast<uint16_t *>(smem);
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(blob);

@@ -56,6 +56,15 @@ struct DecodeIO {
     int *fail_shot;          // [fail_cap]
     double *fail_llr;        // [fail_cap][n]
     int fail_cap;
+    // indirection (second pass of the lane-per-shot min-sum path): when shot_list is set, dispenser position k stands for
+    // shot shot_list[k] and the number of positions is *list_len (device memory); otherwise position k is shot k of `shots`
+    const int *shot_list;
+    const int *list_len;
+    // lane-per-shot kernel only: shots still running after `defer_iters` (< max_iter) iterations are abandoned and appended
+    // here (position counter + list) for a warp-per-shot pass that decodes them from scratch
+    int *defer_count;
+    int *defer_list;
+    int defer_iters;
 };
 
 struct MsConst {

@@ -21,7 +21,7 @@ __device__ __forceinline__ uint32_t get_bit(const uint32_t *w, int i) { return (
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bf_decode_kernel(GraphDev g, int max_iter, DecodeIO io)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per = g.nw + 2 * g.mw;
     uint32_t *eb = reinterpret_cast<uint32_t *>(smem) + (size_t)warp * per;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) bf_decode_kernel(GraphDev g, int max_iter
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ng_decode_kernel(GraphDev g, DecodeIO io)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per = g.nw + g.mw + g.n;
     uint32_t *eb = reinterpret_cast<uint32_t *>(smem) + (size_t)warp * per;

@@ -284,11 +284,16 @@ __global__ void __launch_bounds__(kMsMaxWarps * 32, 1) ms_decode_kernel(MsTables
     const float Tf = c.Tf;
     const bool init_bit = 0.0f < Tf;                    // decision of a variable whose sum is still 0 (only if L < 0)
 
+    const long long n_pos = io.shot_list ? (long long)*io.list_len : io.shots;
     for (;;) {
         long long shot = 0;
-        if (lane == 0) shot = (long long)atomicAdd(io.work_counter, 1ull);
+        if (lane == 0) {
+            shot = (long long)atomicAdd(io.work_counter, 1ull);
+            if (io.shot_list && shot < n_pos) shot = io.shot_list[shot];
+            else if (io.shot_list) shot = -1;
+        }
         shot = __shfl_sync(full, shot, 0);
-        if (shot >= io.shots) break;
+        if (shot < 0 || shot >= io.shots) break;
 
         // ---- initial state: c2v = 0 (decoders.py:150), S = 0, residual = syndrome (+ H.1 if the all-zero sums decide 1)
         for (int i = lane * 4; i < lay.zero_words; i += 128)

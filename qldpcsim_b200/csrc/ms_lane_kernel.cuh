@@ -16,7 +16,10 @@
 //   * the reference's full posterior sweep after the very first layer step is a no-op for untouched variables when the
 //     prior is non-negative (S_j = 0 decides 0), so it is skipped; plans with a negative prior use the warp kernel;
 //   * a lane whose shot finishes mid-iteration idles until the next iteration boundary, where finished lanes fetch new
-//     shots with one aggregated atomic.
+//     shots with one aggregated atomic;
+//   * a lock-step layer step costs ~10 us of dependent L2/HBM round trips, so a shot that does not converge would hold
+//     its lane for max_iter * layers steps (225 ms for LP118_2, 50 iterations) and, at the tail of a batch, keep a whole
+//     SM waiting: shots still running after `defer_iters` iterations are handed to the warp-per-shot kernel instead.
 #pragma once
 #include "common.cuh"
 
@@ -46,7 +49,7 @@ template <int DC, int DV>
 __global__ void __launch_bounds__(256, 2) ms_lane_kernel(LaneTables t, const uint16_t *__restrict__ blob, MsConst c, DecodeIO io,
                                                         LaneScratch sc)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     uint16_t *tab = reinterpret_cast<uint16_t *>(smem);
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(blob);
@@ -217,6 +220,13 @@ __global__ void __launch_bounds__(256, 2) ms_lane_kernel(LaneTables t, const uin
         }
         // ---------------- end of the iteration
         if (!done) ++it;
+        // hand-over: a shot that needs more than defer_iters iterations would pin its lane (and, at the tail of the batch, its
+        // whole warp) for max_iter slow lock-step iterations; it is abandoned here and decoded from scratch by the
+        // warp-per-shot kernel, which is bit-identical
+        const bool defer_now = !done && io.defer_list && it >= io.defer_iters && it < c.max_iter;
+        if (__any_sync(full, defer_now)) {
+            if (defer_now) { io.defer_list[atomicAdd(io.defer_count, 1)] = (int)shot; done = true; }
+        }
         const bool fail_now = !done && it >= c.max_iter;                                               // :182
         if (__any_sync(full, fail_now)) {
             int slot = -1;

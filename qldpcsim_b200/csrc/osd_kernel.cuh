@@ -12,8 +12,17 @@
 //      bits are the unique solution of H_J e_J = s + H_I e_I                           (decoders.py:347-368)
 // Implementation: the matrix is NOT permuted; rows stay bit-packed in original column numbering with one
 // extra word for the right-hand side, initialised to the residual syndrome s + H e.  Solving for the basis
-// FLIPS d_J (H_J d_J = residual) is equivalent and needs no knowledge of I before the elimination.  Pivot
-// search uses warp ballots over the candidate rows; the row updates run over (row, word) pairs.
+// FLIPS d_J (H_J d_J = residual) is equivalent and needs no knowledge of I before the elimination.
+//   * FORWARD elimination only (the pivot column is cleared from the rows that are not pivot rows yet), then a
+//     back-substitution by one warp: half the row operations of Gauss-Jordan, same (unique) solution;
+//   * warp per row, lane per 32-bit word: a row is touched only if it holds the pivot bit (one broadcast load
+//     decides for the warp), the pivot row is held in registers, unused rows are kept as a compacted index list
+//     that shrinks with every pivot;
+//   * the same pass ORs the updated rows into `live` words: a column whose live bit is clear has no pivot among
+//     the unused rows, so dependent columns are skipped 32 at a time by a ballot instead of costing a pivot search
+//     and two barriers each;
+//   * two CTA barriers per pivot (pivot row known / rows updated); the scratch words they protect are double
+//     buffered by iteration parity.
 #pragma once
 #include "common.cuh"
 
@@ -42,9 +51,11 @@ __device__ __forceinline__ double osd_reliability(double llr)
 }
 
 constexpr int kOsdThreads = 256;
+constexpr int kOsdWarps = kOsdThreads / 32;
+constexpr int kOsdMaxTrips = 2;           // words per lane: rows of up to 64 words (n <= 2016)
 
-// dynamic shared memory: A [m][nw+1] uint32 | rel [n] double | perm [n] int | used [m] uint8 (as uint32 words)
-// | pivrow [n] int16-ish (int)   -- sized by osd_smem_bytes()
+// dynamic shared memory: A [m][nw+1] uint32 | rel [n] double | perm [n] int | pivrow [n] int | rows [m] int |
+// pcol [m] int | prow [m] int | live [2][rw] | scalars   -- sized by osd_smem_bytes()
 inline size_t osd_smem_bytes(int m, int n, int nw)
 {
     size_t b = (size_t)m * (nw + 1) * 4;
@@ -52,23 +63,32 @@ inline size_t osd_smem_bytes(int m, int n, int nw)
     b += (size_t)n * 8;      // rel
     b += (size_t)n * 4;      // perm
     b += (size_t)n * 4;      // pivot row of column (or -1)
-    b += (size_t)m * 4;      // row used flag
+    b += (size_t)m * 4 * 3;  // unused-row list, pivot columns, pivot rows (in pivot order)
+    b += (size_t)(nw + 1) * 4 * 2;   // live words, double buffered
     return b + 64;
 }
 
+// TRIPS = ceil((nw + 1) / 32): words of an augmented row per lane
+template <int TRIPS>
 __global__ void __launch_bounds__(kOsdThreads) osd_kernel(OsdArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int kOsdTrips = TRIPS;
+    extern __shared__ __align__(128) unsigned char smem[];
     const int m = a.m, n = a.n, nw = a.nw, rw = a.nw + 1;   // rw: words per augmented row
     uint32_t *A = reinterpret_cast<uint32_t *>(smem);
     size_t off = ((size_t)m * rw * 4 + 7) & ~size_t(7);
     double *rel = reinterpret_cast<double *>(smem + off); off += (size_t)n * 8;
     int *perm = reinterpret_cast<int *>(smem + off); off += (size_t)n * 4;
     int *pivrow = reinterpret_cast<int *>(smem + off); off += (size_t)n * 4;
-    int *used = reinterpret_cast<int *>(smem + off); off += (size_t)m * 4;
-    int *sh = reinterpret_cast<int *>(smem + off);          // sh[0]: pivot row candidate, sh[1]: rank so far
-    const int tid = threadIdx.x, lane = tid & 31;
+    int *rows = reinterpret_cast<int *>(smem + off); off += (size_t)m * 4;
+    int *pcol = reinterpret_cast<int *>(smem + off); off += (size_t)m * 4;
+    int *prowl = reinterpret_cast<int *>(smem + off); off += (size_t)m * 4;
+    uint32_t *live = reinterpret_cast<uint32_t *>(smem + off); off += (size_t)rw * 4 * 2;
+    int *sh = reinterpret_cast<int *>(smem + off);          // sh[0..1]: pivot candidate (list position), double buffered
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned full = 0xffffffffu;
     const int count = a.count_dev ? min(*a.count_dev, a.count) : a.count;
+    const int INF = 0x7fffffff;
 
     for (int item = blockIdx.x; item < count; item += gridDim.x) {
         const long long shot = a.shot_ids ? a.shot_ids[item] : item;
@@ -81,7 +101,9 @@ __global__ void __launch_bounds__(kOsdThreads) osd_kernel(OsdArgs a)
             A[i * rw + w] = a.hbits[x];
         }
         for (int j = tid; j < n; j += kOsdThreads) { rel[j] = osd_reliability(llr[j]); pivrow[j] = -1; }
-        for (int i = tid; i < m; i += kOsdThreads) used[i] = 0;
+        for (int i = tid; i < m; i += kOsdThreads) rows[i] = i * rw;          // unused-row list: word offset of the row
+        for (int w = tid; w < 2 * rw; w += kOsdThreads) live[w] = 0u;
+        if (tid == 0) { sh[0] = INF; sh[1] = INF; }
         __syncthreads();
         for (int i = tid; i < m; i += kOsdThreads) {
             uint32_t par = 0;
@@ -100,68 +122,123 @@ __global__ void __launch_bounds__(kOsdThreads) osd_kernel(OsdArgs a)
                 perm[rank] = j;
             }
         }
-        if (tid == 0) { sh[1] = 0; }
+        // ---- live words of the untouched matrix (buffer 0)
+        {
+            uint32_t acc[kOsdTrips] = {};
+            for (int i = warp; i < m; i += kOsdWarps)
+#pragma unroll
+                for (int t = 0; t < kOsdTrips; ++t) { const int w = lane + 32 * t; if (w < nw) acc[t] |= A[i * rw + w]; }
+#pragma unroll
+            for (int t = 0; t < kOsdTrips; ++t) { const int w = lane + 32 * t; if (w < nw && acc[t]) atomicOr(&live[w], acc[t]); }
+        }
         __syncthreads();
-        // ---- Gauss-Jordan in the given column order
-        int rank = 0;
+        // ---- forward elimination in the given column order
+        int rank = 0, nun = m, cpos = 0, it = 0;
         int first_info = -1;                                     // first non-pivot column met (order-1 flip)
-        for (int cpos = 0; cpos < n && rank < a.rank_h; ++cpos) {
-            const int col = perm[cpos];
+        while (rank < a.rank_h && cpos < n) {
+            const uint32_t *lv = live + (it & 1) * rw;
+            uint32_t *lv_next = live + ((it + 1) & 1) * rw;
+            // next column, in order, that still has a 1 in an unused row (every warp computes the same result)
+            int found = -1;
+            while (cpos < n) {
+                const int c = cpos + lane;
+                bool bit = false;
+                if (c < n) { const int col = perm[c]; bit = (lv[col >> 5] >> (col & 31)) & 1u; }
+                const uint32_t valid = (n - cpos >= 32) ? full : ((1u << (n - cpos)) - 1u);
+                const uint32_t bal = __ballot_sync(full, bit);
+                const uint32_t clear_before = ~bal & valid & (bal ? ((1u << (__ffs(bal) - 1)) - 1u) : full);
+                if (first_info < 0 && clear_before) first_info = perm[cpos + __ffs(clear_before) - 1];
+                if (bal) { found = cpos + __ffs(bal) - 1; break; }
+                cpos += 32;
+            }
+            if (found < 0) break;
+            const int col = perm[found];
             const int cw = col >> 5;
             const uint32_t cb = 1u << (col & 31);
-            if (tid == 0) sh[0] = 0x7fffffff;
-            __syncthreads();
-            // pivot: lowest-index unused row with a 1 in this column (any choice gives the same solution)
-            for (int i0 = 0; i0 < m; i0 += kOsdThreads) {
-                const int i = i0 + tid;
-                const bool hit = (i < m) && !used[i] && (A[i * rw + cw] & cb);
-                const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-                if (bal && lane == 0) atomicMin(&sh[0], i0 + (tid & ~31) + (__ffs(bal) - 1));
+            // pivot: any unused row with a 1 in this column (the solution does not depend on the choice); lowest list position
+            for (int x0 = 0; x0 < nun; x0 += kOsdThreads) {
+                const int x = x0 + tid;
+                const bool hit = (x < nun) && (A[rows[x < nun ? x : 0] + cw] & cb);
+                const uint32_t bal = __ballot_sync(full, hit);
+                if (bal && lane == 0) atomicMin(&sh[it & 1], x0 + (tid & ~31) + (__ffs(bal) - 1));
             }
+            if (tid < rw) lv_next[tid] = 0u;                     // rw <= 64 < kOsdThreads; nobody reads this buffer any more
             __syncthreads();
-            const int prow = sh[0];
-            if (prow == 0x7fffffff) {                            // dependent column -> information set
-                if (first_info < 0) first_info = col;
-                __syncthreads();
-                continue;
-            }
-            // eliminate the column from every other row: (row, word) pairs, pivot row read-only
-            for (int x = tid; x < m * rw; x += kOsdThreads) {
-                const int i = x / rw, w = x - i * rw;
-                if (i != prow && (A[i * rw + cw] & cb)) {
-                    // the word holding the pivot bit is cleared last by the thread that owns it, so every
-                    // thread of this row still sees the bit set: defer that word
-                    if (w != cw) A[x] ^= A[prow * rw + w];
+            const int pidx = sh[it & 1];
+            if (pidx == INF) break;                              // cannot happen: a set live bit means an unused row holds the column
+            const int prow = rows[pidx];                         // word offset of the pivot row
+            uint32_t pw[kOsdTrips], acc[kOsdTrips] = {};
+#pragma unroll
+            for (int t = 0; t < kOsdTrips; ++t) { const int w = lane + 32 * t; pw[t] = (w < rw) ? A[prow + w] : 0u; }
+            const int cl = cw & 31, ct = cw >> 5;                // lane / trip that holds the pivot word of a row
+            // two rows per trip of the loop (independent loads in flight); a row is updated only if it holds the pivot bit,
+            // which its own pivot word tells (one shuffle, no extra load)
+            for (int x = warp; x < nun; x += 2 * kOsdWarps) {
+                const int x2 = x + kOsdWarps;
+                const bool ok1 = x != pidx, ok2 = x2 < nun && x2 != pidx;          // warp-uniform
+                const int i1 = rows[x], i2 = rows[x2 < nun ? x2 : x];
+                uint32_t v1[kOsdTrips], v2[kOsdTrips];
+#pragma unroll
+                for (int t = 0; t < kOsdTrips; ++t) {
+                    const int w = lane + 32 * t;
+                    const bool in = (t + 1 < kOsdTrips) || (w < rw);
+                    v1[t] = in ? A[i1 + w] : 0u;
+                    v2[t] = in ? A[i2 + w] : 0u;
+                }
+                uint32_t k1 = v1[0], k2 = v2[0];
+#pragma unroll
+                for (int t = 1; t < kOsdTrips; ++t) { k1 = (ct == t) ? v1[t] : k1; k2 = (ct == t) ? v2[t] : k2; }
+                const bool has1 = ok1 && (__shfl_sync(full, k1, cl) & cb);
+                const bool has2 = ok2 && (__shfl_sync(full, k2, cl) & cb);
+#pragma unroll
+                for (int t = 0; t < kOsdTrips; ++t) {
+                    const int w = lane + 32 * t;
+                    const bool in = (t + 1 < kOsdTrips) || (w < rw);
+                    if (has1) { v1[t] ^= pw[t]; if (in) A[i1 + w] = v1[t]; }
+                    if (has2) { v2[t] ^= pw[t]; if (in) A[i2 + w] = v2[t]; }
+                    const bool data = (t + 1 < kOsdTrips) ? true : (w < nw);       // the right-hand-side word is not a column
+                    if (data) acc[t] |= (ok1 ? v1[t] : 0u) | (ok2 ? v2[t] : 0u);
                 }
             }
+#pragma unroll
+            for (int t = 0; t < kOsdTrips; ++t) { const int w = lane + 32 * t; if (w < nw && acc[t]) atomicOr(&lv_next[w], acc[t]); }
+            if (tid == 0) {
+                rows[pidx] = rows[nun - 1];                       // entry pidx is skipped by every reader of this pass
+                pcol[rank] = col; prowl[rank] = prow; pivrow[col] = prow / rw;
+                sh[(it + 1) & 1] = INF;
+            }
             __syncthreads();
-            for (int i = tid; i < m; i += kOsdThreads)
-                if (i != prow && (A[i * rw + cw] & cb)) A[i * rw + cw] ^= A[prow * rw + cw];
-            if (tid == 0) { used[prow] = 1; pivrow[col] = prow; }
-            ++rank;
-            __syncthreads();
+            ++rank; --nun; ++it; cpos = found + 1;
         }
         // remaining columns (the loop stops once rank(H) columns are kept) are information columns
         if (first_info < 0) {
-            for (int cpos = 0; cpos < n; ++cpos) if (pivrow[perm[cpos]] < 0) { first_info = perm[cpos]; break; }
+            for (int c = 0; c < n; ++c) if (pivrow[perm[c]] < 0) { first_info = perm[c]; break; }
         }
-        __syncthreads();
-        // ---- order 1: flip the first information bit (App. B-8) and add its reduced column to the rhs
+        // ---- order 1: flip the first information bit (App. B-8) and move its column to the right-hand side
         if (a.order == 1 && first_info >= 0) {
             const int cw = first_info >> 5;
             const uint32_t cb = 1u << (first_info & 31);
             for (int i = tid; i < m; i += kOsdThreads) if (A[i * rw + cw] & cb) A[i * rw + nw] ^= 1u;
             if (tid == 0) e[cw] ^= cb;
-            __syncthreads();
         }
-        // ---- basis flips: d_col = rhs[pivot row of col]
-        for (int w = tid; w < nw; w += kOsdThreads) {
-            uint32_t flip = 0;
-            for (int b = 0; b < 32; ++b) {
-                const int j = w * 32 + b;
-                if (j < n) { const int pr = pivrow[j]; if (pr >= 0 && (A[pr * rw + nw] & 1u)) flip |= 1u << b; }
+        __syncthreads();
+        // ---- back-substitution (warp 0): pivot r's row holds 1s only in its own column, in LATER pivot columns and in
+        // information columns (whose flips are 0): d_col = rhs + <row, d>
+        if (warp == 0) {
+            uint32_t d[kOsdTrips] = {};
+            for (int r = rank - 1; r >= 0; --r) {
+                const int pr = prowl[r], col = pcol[r];
+                uint32_t par = 0;
+#pragma unroll
+                for (int t = 0; t < kOsdTrips; ++t) { const int w = lane + 32 * t; if (w < nw) par ^= A[pr + w] & d[t]; }
+                const uint32_t odd = __popc(__ballot_sync(full, __popc(par) & 1u)) & 1u;
+                const uint32_t bit = (A[pr + nw] & 1u) ^ odd;
+                const int cw = col >> 5;
+#pragma unroll
+                for (int t = 0; t < kOsdTrips; ++t) if (bit && lane == (cw & 31) && (cw >> 5) == t) d[t] |= 1u << (col & 31);
             }
-            e[w] ^= flip;
+#pragma unroll
+            for (int t = 0; t < kOsdTrips; ++t) { const int w = lane + 32 * t; if (w < nw) e[w] ^= d[t]; }
         }
         __syncthreads();
     }
@@ -170,16 +247,13 @@ __global__ void __launch_bounds__(kOsdThreads) osd_kernel(OsdArgs a)
 inline int osd_launch(const OsdArgs &a, int sm_count, cudaStream_t st)
 {
     const size_t smem = osd_smem_bytes(a.m, a.n, a.nw);
-    if (smem > (size_t)kMaxSmemPerCta) return (int)cudaErrorInvalidValue;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(osd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = smem;
-    }
+    if (smem > (size_t)kMaxSmemPerCta || a.nw + 1 > 32 * kOsdMaxTrips) return (int)cudaErrorInvalidValue;
+    void (*fn)(OsdArgs) = (a.nw + 1 <= 32) ? osd_kernel<1> : osd_kernel<2>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemPerCta);
+    if (e != cudaSuccess) return (int)e;
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)kMaxSmemPerCta / smem));
     const int grid = std::max(1, std::min(a.count, sm_count * per_sm));
-    osd_kernel<<<grid, kOsdThreads, smem, st>>>(a);
+    fn<<<grid, kOsdThreads, smem, st>>>(a);
     return (int)cudaGetLastError();
 }
 

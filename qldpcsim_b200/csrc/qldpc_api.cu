@@ -598,6 +598,7 @@ static int launch_decode(qldpc_plan *p, const uint32_t *syn, int64_t shots, uint
     io.syn = syn; io.ehat = ehat; io.iters = iters; io.conv = conv; io.llr = llr; io.shots = shots;
     io.work_counter = p->d_work + slot;
     io.fail_count = fail_count; io.fail_shot = fail_shot; io.fail_llr = fail_llr; io.fail_cap = fail_cap;
+    io.shot_list = nullptr; io.list_len = nullptr; io.defer_count = nullptr; io.defer_list = nullptr; io.defer_iters = 0;
     CU_TRY(cudaMemsetAsync(p->d_work + slot, 0, sizeof(unsigned long long), st));
     const int grid = (int)std::min<int64_t>(p->grid, (shots + p->shots_per_cta - 1) / p->shots_per_cta);
     const qldpc_opts &o = p->opts;
@@ -611,10 +612,12 @@ static int launch_decode(qldpc_plan *p, const uint32_t *syn, int64_t shots, uint
             if ((double)f < T) f = std::nextafterf(f, INFINITY);
             c.Tf = f;
         }
-        // automatic choice: the lane kernel only pays off once the batch is many waves deep (measured: 1.5x at 10^6 shots,
-        // slower at 10^5 because a non-converging shot pins its whole warp for max_iter iterations at the tail)
-        if (p->use_lane && (p->lane_forced || shots >= 500000)) {
-            const PlanKernels *pk = kernels_of(p);
+        // automatic choice: the lane kernel needs a batch that fills its grid (2 CTAs x 8 warps x 32 shots per SM).  Measured on
+        // LP118_2 serial, p = 0.05, with the hand-over of slow shots: 1.61M vs 0.88M shots/s (warp kernel) at 10^6 shots,
+        // 0.91M vs 0.74M at 10^5 shots (with OSD)
+        static const int force = [] { const char *ev = getenv("QLDPC_MS_KERNEL"); return !ev ? 0 : (ev[0] == 'w' ? 1 : (ev[0] == 'l' ? 2 : 0)); }();   // tuning knob
+        if (p->use_lane && force != 1 && (p->lane_forced || force == 2 || shots >= 65536)) {
+            PlanKernels *pk = kernels_of(p);
             const LaneTables &lt = pk->lane_tab;
             const int lgrid = (int)std::min<int64_t>(p->lane_grid, (shots + 255) / 256);
             const size_t warps = (size_t)lgrid * 8;
@@ -626,7 +629,26 @@ static int launch_decode(qldpc_plan *p, const uint32_t *syn, int64_t shots, uint
             unsigned char *sb = (unsigned char *)p->scratch[3];
             sc.c2v = (float *)sb; sc.S = (float *)(sb + b_c2v); sc.par = (uint32_t *)(sb + b_c2v + b_S);
             sc.eb = (uint32_t *)(sb + b_c2v + b_S + b_par);
+            // shots that need more than kLaneIters iterations are deferred to the warp-per-shot kernel (second launch below)
+            constexpr int kLaneIters = 6;
+            const bool defer = o.max_iter > kLaneIters;
+            if (defer) {
+                if ((rc2 = ensure_scratch(p, 4, (size_t)shots * sizeof(int) + 16))) return rc2;
+                io.defer_count = (int *)p->scratch[4];
+                io.defer_list = (int *)p->scratch[4] + 4;
+                io.defer_iters = kLaneIters;
+                CU_TRY(cudaMemsetAsync(io.defer_count, 0, sizeof(int), st));
+            }
             pk->ms_lane<<<lgrid, 256, p->lane_smem, st>>>(lt, p->d_lane_blob, c, io, sc);
+            if (defer) {
+                g_launches++;
+                CU_TRY(cudaGetLastError());
+                DecodeIO io2 = io;
+                io2.shot_list = io.defer_list; io2.list_len = io.defer_count;
+                io2.defer_count = nullptr; io2.defer_list = nullptr;
+                CU_TRY(cudaMemsetAsync(p->d_work + slot, 0, sizeof(unsigned long long), st));
+                pk->ms<<<p->grid, p->threads, p->smem_bytes, st>>>(pk->ms_tab, p->d_blob, c, io2);
+            }
         } else {
             kernels_of(p)->ms<<<grid, p->threads, p->smem_bytes, st>>>(kernels_of(p)->ms_tab, p->d_blob, c, io);
         }
@@ -663,7 +685,9 @@ int qldpc_decode(qldpc_plan *p, const uint32_t *syn, int64_t shots, uint32_t *eh
     if (!(osd || osd_bp)) return launch_decode(p, syn, shots, ehat, iters, conv, llr, nullptr, nullptr, nullptr, 0, 0, st);
     // With OSD the batch is processed in chunks so that the compacted LLR buffer of the unconverged shots
     // stays bounded: chunk * n * 8 bytes.
-    const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(shots, (int64_t)(256ll << 20) / ((int64_t)p->tab.n * 8)));
+    // the compacted LLR buffer holds one row per shot of the chunk (a chunk in which every shot fails cannot overflow it);
+    // up to 2 GiB of the 180 GB are spent on it so that a chunk stays many waves deep (LP118_2: 263k shots per chunk)
+    const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(shots, (int64_t)(2048ll << 20) / ((int64_t)p->tab.n * 8)));
     int rc;
     if ((rc = ensure_scratch(p, 0, (size_t)chunk * sizeof(int)))) return rc;
     if ((rc = ensure_scratch(p, 1, (size_t)chunk * p->tab.n * sizeof(double)))) return rc;

@@ -50,7 +50,7 @@ __host__ __device__ inline void pauli_thresholds(double p, unsigned long long t[
 
 __global__ void __launch_bounds__(256) sample_kernel(SampleArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nw = a.gz.nw, n = a.gz.n;
     uint32_t *ex = reinterpret_cast<uint32_t *>(smem) + (size_t)warp * 2 * nw;
