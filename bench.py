@@ -8,7 +8,7 @@ layered schedule, 50 iterations, OSD off, depolarizing p = 0.05, 10^6 shots per 
 
 One "step" = one pass of the hot path over one resident batch: decode the X errors (plan on Hz), decode the Z errors
 (plan on Hx), classify + count (simulator.py:244-304 of the reference), followed by the one collective of the path,
-an all-reduce of the int64[8] counters.  Prints ONE JSON line on rank 0.
+an all-reduce of the int64[10] counters.  Prints ONE JSON line on rank 0.
 
   value     : shots/s with the bit-packed syndromes/errors already in HBM (device sampler, untimed), CUDA events,
               max over ranks.
@@ -45,8 +45,8 @@ DEC_ITERS = 50
 SCHEDULE = "L"
 SHOTS_PER_STEP = 1_000_000
 BYTES_PER_EDGE_ITER = 16.0          # layered / serial: c2v read+write, posterior read+write
-CPU_SAMPLE_SHOTS = 32768
-REF_STEP_SHOTS = 8192
+CPU_SAMPLE_SHOTS = 262144         # cpu_baseline leg: ~3.5 s wall on 16 host threads (~1 core-minute)
+REF_STEP_SHOTS = 65536            # --impl reference: ~0.9 s per step on 16 host threads
 METRIC = "shots/sec decoded (X+Z), LP118_0 MS-layered 50 it"
 UNIT = "shots/s"
 
@@ -210,7 +210,7 @@ def run_gpu(args):
                                       outZ[0].data_ptr(), synz.data_ptr(), synx.data_ptr(), outX[1].data_ptr(), outZ[1].data_ptr(),
                                       shots, counters.data_ptr(), st.cuda_stream))
         if world > 1:
-            dist.all_reduce(counters)          # the path's only collective (64 bytes); counters are re-zeroed per step
+            dist.all_reduce(counters)          # the path's only collective (80 bytes); counters are re-zeroed per step
 
     def barrier():
         if world > 1:
@@ -295,7 +295,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": shots * 4 * (mzw + mxw),
                     "d2h_bytes_per_step": shots * 2 * (4 * nw + 4 + 1), "api": "qldpc_decode_host (pinned host buffers), X then Z"},
             "gpu_launches": int(launches) * world,
-            "roofline": {"bound": "hbm", "kernel": "ms_decode_kernel<8,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "ms_decode_kernel<8,true,5,3>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src,
                          "bytes_per_edge_iteration": BYTES_PER_EDGE_ITER, "kernel_ms_per_step": tX + tZ,
                          "kernel_share_of_step": (tX + tZ) / (elapsed_ms / args.steps),

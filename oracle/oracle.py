@@ -230,9 +230,13 @@ def simulate_p(Hx: np.ndarray, Hz: np.ndarray, record: np.ndarray, p: float, dec
     exact = np.all(eX == errX, axis=1) & np.all(eZ == errZ, axis=1)                       # :294-295
     dX = (errX.astype(np.int64) ^ eX)
     dZ = (errZ.astype(np.int64) ^ eZ)
-    degen = (~exact) & np.all(dX @ Hz.T.astype(np.int64) == 0, axis=1) & np.all(dZ @ Hx.T.astype(np.int64) == 0, axis=1)  # :296-298 (no mod 2)
-    failX = np.any((eX.astype(np.int64) @ Hz.T.astype(np.int64)) % 2 != sy_z, axis=1)    # :300-301
-    failZ = np.any((eZ.astype(np.int64) @ Hx.T.astype(np.int64)) % 2 != sy_x, axis=1)    # :302-303
+
+    def imat(a, Ht):
+        # integer matrix product through BLAS: the entries are counts <= n < 2^24, exactly representable in binary32
+        return np.rint(a.astype(np.float32) @ Ht.astype(np.float32)).astype(np.int64)
+    degen = (~exact) & np.all(imat(dX, Hz.T) == 0, axis=1) & np.all(imat(dZ, Hx.T) == 0, axis=1)   # :296-298 (no mod 2)
+    failX = np.any(imat(eX, Hz.T) % 2 != sy_z, axis=1)                                    # :300-301
+    failZ = np.any(imat(eZ, Hx.T) % 2 != sy_x, axis=1)                                    # :302-303
     res = {
         "DecFailures_X": int(failX.sum()),
         "DecFailures_Z": int(failZ.sum()),

@@ -146,6 +146,8 @@ ORACLE_CASES = [
     ("LP04_0", "MS", "F", 0.08, 5000, 50),
     ("LP04_0", "MS", "S", 0.05, 2000, 50),
     ("LP118_0", "MS", "L", 0.05, 10000, 50),
+    ("LP118_0", "MS", "L", 0.05, 100000, 50),      # the headline configuration, 10^5 shots bit for bit
+    ("LP118_2", "MS", "S", 0.05, 70000, 50),       # batch large enough for the automatic lane-per-shot path + hand-over
     ("LP118_0", "MS", "L", 0.10, 3000, 50),
     ("LP118_0", "MS", "F", 0.05, 4000, 50),
     ("LP118_2", "MS", "L", 0.05, 2000, 50),
