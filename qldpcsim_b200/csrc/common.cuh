@@ -79,6 +79,11 @@ struct MsConst {
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// bit-packed column arrays (columns of H, of the logical bases): one 128-byte line per column, of which the classifier reads
+// the first col_words(words) words with 1, 2, 4 or 8 128-bit loads
+constexpr int kColStride = 32;
+__host__ __device__ inline int col_words(int words) { return words <= 4 ? 4 : (words <= 8 ? 8 : (words <= 16 ? 16 : 32)); }
+
 }  // namespace qldpc
 
 // Host-side plan object (opaque to C callers).
@@ -97,8 +102,8 @@ struct qldpc_plan {
     size_t lane_smem = 0;
     int32_t *d_row_ptr = nullptr, *d_col_idx = nullptr, *d_col_ptr = nullptr, *d_row_idx = nullptr;
     uint32_t *d_hbits = nullptr;   // [m][nw] bit-packed rows of H (OSD, sampler, classification)
-    uint32_t *d_hcol = nullptr;    // [n][mw] bit-packed columns of H (syndrome of a sparse vector)
-    uint32_t *d_lcol = nullptr;    // [n][lkw] bit-packed columns of the attached logical-operator basis (or null)
+    uint32_t *d_hcol = nullptr;    // [n][kColStride] bit-packed columns of H (syndrome of a sparse vector), zero padded
+    uint32_t *d_lcol = nullptr;    // [n][kColStride] bit-packed columns of the attached logical-operator basis (or null)
     int logical_k = 0, lkw = 0;
     unsigned long long *d_work = nullptr;
     int *d_fail_count = nullptr;

@@ -144,67 +144,59 @@ __global__ void __launch_bounds__(256) ng_decode_kernel(GraphDev g, DecodeIO io)
 //   degen : not exact and Hz (errX^eX) == 0 and Hx (errZ^eZ) == 0 as INTEGER products, i.e. the difference
 //           touches no check at all (:296-298, no mod 2) <=> diff & colmask == 0, colmask = OR of the rows
 //   failX : sy_z != Hz eX mod 2 (:300-301),  failZ : sy_x != Hx eZ mod 2 (:302-303)
-// One warp per shot (grid-stride); counters accumulated per CTA then atomically into int64[8].
+// One warp per shot (grid-stride); counters accumulated per CTA then atomically into int64[QLDPC_NUM_COUNTERS].
 // ---------------------------------------------------------------------------------------------------------
 struct ClassifyArgs {
     GraphDev gz, gx;                       // gz = Hz (X-error decode), gx = Hx (Z-error decode)
     const uint32_t *colmask_z, *colmask_x; // [nw] OR of the rows of Hz / Hx
-    const uint32_t *hcol_z, *hcol_x;       // [n][mw] bit-packed columns of Hz / Hx
-    const uint32_t *lcol_z, *lcol_x;       // [n][kw] bit-packed columns of the logical-Z / logical-X bases, or null
-    int kwz, kwx;                          // words(k) of the two bases
+    const uint32_t *hcol_z, *hcol_x;       // [n][kColStride] bit-packed columns of Hz / Hx, zero padded
+    const uint32_t *lcol_z, *lcol_x;       // [n][kColStride] bit-packed columns of the logical-Z / logical-X bases, or null
     const uint32_t *errx, *errz, *ehx, *ehz, *synz, *synx;
     const int32_t *itx, *itz;
     long long shots;
     unsigned long long *counters;
 };
 
-// H e (mod 2) by XOR-ing the bit-packed COLUMNS of H selected by the set bits of e (the estimates are sparse: ~2pn/3
-// bits), one syndrome word per lane; returns whether it differs from `syn`.  hcol: [n][mw] words.  Needs mw <= 32.
-__device__ __forceinline__ bool syndrome_mismatch(const GraphDev &g, const uint32_t *__restrict__ hcol, const uint32_t *e /*global [nw]*/,
-                                                  const uint32_t *syn /*global [mw]*/, int lane)
+// M d (mod 2) for a sparse bit-packed vector d = x ^ y (y may be null), as the XOR of the bit-packed COLUMNS of M selected
+// by the set bits of d (the estimates and residuals are sparse: ~2pn/3 bits).  Every lane walks the set bits of its own
+// word(s) of d and XORs whole columns (V4 128-bit loads each) into private registers -- no cross-lane traffic per bit --
+// and the 4*V4 result words are combined at the end with one warp XOR-reduction (REDUX) each, XOR-ed with `init` (the
+// syndrome words, or null) and tested for zero.  cols: [n][kColStride] words (one 128-byte line per column, zero padded), of
+// which the first 4*V4 are read.
+template <int V4>
+__device__ __forceinline__ bool xor_columns_nonzero(const uint4 *__restrict__ cols, int nw, const uint32_t *x, const uint32_t *y,
+                                                    const uint32_t *init, int init_words, int lane)
 {
-    uint32_t acc = (lane < g.mw) ? syn[lane] : 0u;
-    const uint32_t mine = (lane < g.nw) ? e[lane] : 0u;
-    for (int w0 = 0; w0 < g.nw; w0 += 32) {
-        const uint32_t word_l = (w0 == 0) ? mine : ((w0 + lane < g.nw) ? e[w0 + lane] : 0u);
-        uint32_t nz = __ballot_sync(0xffffffffu, word_l != 0u);
-        while (nz) {                                        // warp-uniform loops: words, then their set bits
-            const int wl = __ffs(nz) - 1;
-            nz &= nz - 1;
-            uint32_t bits = __shfl_sync(0xffffffffu, word_l, wl);
-            while (bits) {
-                const int j = (w0 + wl) * 32 + __ffs(bits) - 1;
-                bits &= bits - 1;
-                if (lane < g.mw) acc ^= hcol[(size_t)j * g.mw + lane];
-            }
-        }
-    }
-    return __any_sync(0xffffffffu, acc != 0u);
-}
-
-// L d (mod 2) != 0 for d = x ^ y (two bit-packed vectors in global memory), by XOR-ing the bit-packed COLUMNS of L selected
-// by the set bits of d, one word of the result per lane.  lcol: [n][kw] words, kw <= 32.
-__device__ __forceinline__ bool anticommutes_with_logical(const uint32_t *__restrict__ lcol, int kw, int nw, const uint32_t *x,
-                                                          const uint32_t *y, int lane)
-{
-    uint32_t acc = 0u;
+    uint32_t acc[4 * V4];
+#pragma unroll
+    for (int k = 0; k < 4 * V4; ++k) acc[k] = 0u;
     for (int w0 = 0; w0 < nw; w0 += 32) {
-        const uint32_t word_l = (w0 + lane < nw) ? (x[w0 + lane] ^ y[w0 + lane]) : 0u;
-        uint32_t nz = __ballot_sync(0xffffffffu, word_l != 0u);
-        while (nz) {
-            const int wl = __ffs(nz) - 1;
-            nz &= nz - 1;
-            uint32_t bits = __shfl_sync(0xffffffffu, word_l, wl);
-            while (bits) {
-                const int j = (w0 + wl) * 32 + __ffs(bits) - 1;
-                bits &= bits - 1;
-                if (lane < kw) acc ^= lcol[(size_t)j * kw + lane];
+        uint32_t word = 0u;
+        if (w0 + lane < nw) word = y ? (x[w0 + lane] ^ y[w0 + lane]) : x[w0 + lane];
+        while (__any_sync(0xffffffffu, word != 0u)) {
+            if (word) {
+                const int j = (w0 + lane) * 32 + __ffs(word) - 1;
+                word &= word - 1;
+                const uint4 *c = cols + (size_t)j * (kColStride / 4);
+#pragma unroll
+                for (int v = 0; v < V4; ++v) {
+                    const uint4 q = __ldg(c + v);
+                    acc[4 * v + 0] ^= q.x; acc[4 * v + 1] ^= q.y; acc[4 * v + 2] ^= q.z; acc[4 * v + 3] ^= q.w;
+                }
             }
         }
     }
-    return __any_sync(0xffffffffu, acc != 0u);
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < 4 * V4; ++k) {
+        uint32_t r = __reduce_xor_sync(0xffffffffu, acc[k]);
+        if (init && k < init_words) r ^= init[k];            // warp-uniform (broadcast) load
+        bad |= r != 0u;
+    }
+    return bad;
 }
 
+template <int VH, int VL>
 __global__ void __launch_bounds__(256) classify_kernel(ClassifyArgs a)
 {
     __shared__ unsigned long long cta_cnt[QLDPC_NUM_COUNTERS];
@@ -226,13 +218,14 @@ __global__ void __launch_bounds__(256) classify_kernel(ClassifyArgs a)
         }
         const bool exact = !__any_sync(0xffffffffu, diff);
         const bool degen = !exact && !__any_sync(0xffffffffu, touch);
-        const bool fx = syndrome_mismatch(a.gz, a.hcol_z, hx, a.synz + s * a.gz.mw, lane);
-        const bool fz = syndrome_mismatch(a.gx, a.hcol_x, hz, a.synx + s * a.gx.mw, lane);
+        const bool fx = xor_columns_nonzero<VH>(reinterpret_cast<const uint4 *>(a.hcol_z), nw, hx, nullptr, a.synz + s * a.gz.mw, a.gz.mw, lane);
+        const bool fz = xor_columns_nonzero<VH>(reinterpret_cast<const uint4 *>(a.hcol_x), nw, hz, nullptr, a.synx + s * a.gx.mw, a.gx.mw, lane);
         // README classes (README.md:15-22): the residual of a shot whose two syndromes are reproduced lies in the normaliser;
         // it is a stabiliser iff its X part commutes with every logical Z and its Z part with every logical X
         bool logical = false;
         if (have_logicals && !exact && !fx && !fz)                                   // warp-uniform
-            logical = anticommutes_with_logical(a.lcol_z, a.kwz, nw, ex, hx, lane) | anticommutes_with_logical(a.lcol_x, a.kwx, nw, ez, hz, lane);
+            logical = xor_columns_nonzero<VL>(reinterpret_cast<const uint4 *>(a.lcol_z), nw, ex, hx, nullptr, 0, lane) |
+                      xor_columns_nonzero<VL>(reinterpret_cast<const uint4 *>(a.lcol_x), nw, ez, hz, nullptr, 0, lane);
         if (lane == 0) {
             const bool fail_any = fx | fz;
             c_fa += fail_any;

@@ -247,6 +247,29 @@ __device__ __forceinline__ void ms_var_update2(uint32_t ja4, uint32_t jb4, int l
     }
 }
 
+// Same with FOUR variables per lane (two consecutive pair-trips of the layer's list at once): more independent chains in
+// flight and half the loop overhead for the common layers whose variables fill four sub-groups.
+template <int DV, int DMIN>
+__device__ __forceinline__ void ms_var_update4(uint32_t e0, uint32_t e1, int lane, const MsAddr &A, const MsTables &t, float Tf, int &delta)
+{
+    const uint32_t j4[4] = {e0 & 0xffffu, e0 >> 16, e1 & 0xffffu, e1 >> 16};
+    float s_old[4], s[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) s_old[v] = sld_f32(A.S + j4[v]);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) s[v] = ms_colsum<DV, DMIN>(A.c2v + j4[v], j4[v], t);
+    uint32_t f[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        sst_f32(A.S + j4[v], s[v]);
+        f[v] = __ballot_sync(0xffffffffu, (s[v] < Tf) != (s_old[v] < Tf));      // hard decision flipped (:173-174)
+    }
+    if (f[0] | f[1] | f[2] | f[3]) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) ms_apply_flips(f[v], j4[v], lane, A, delta);
+    }
+}
+
 // DC: instantiated row weight, REGULAR: every row has exactly DC edges, DV: instantiated column weight, DMIN: number of
 // leading regions that hold every variable (0 = guard all).
 template <int DC, bool REGULAR, int DV, int DMIN>
@@ -340,7 +363,10 @@ __global__ void __launch_bounds__(kMsMaxWarps * 32, 1) ms_decode_kernel(MsTables
                 // lane runs the same number of trips (lists are padded to whole trips with the dummy variable n).
                 const int vb = r1 >> 16, ve = r2 & 0xffffu;
                 int delta = 0;
-                for (int q = vb + lane; q < ve; q += 32) {
+                int q = vb + lane;
+                for (; q + 32 < ve; q += 64)
+                    ms_var_update4<DV, DMIN>(sld_u32(lvar + 4u * q), sld_u32(lvar + 4u * q + 128u), lane, A, t, Tf, delta);
+                if (q < ve) {
                     const uint32_t e = sld_u32(lvar + 4u * q);
                     ms_var_update2<DV, DMIN>(e & 0xffffu, e >> 16, lane, A, t, Tf, delta);
                 }

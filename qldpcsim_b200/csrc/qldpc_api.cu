@@ -230,9 +230,11 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
                 hb[(size_t)m * t.nw + (j >> 5)] |= 1u << (j & 31);
             }
         if ((rc = upload(&p->d_hbits, hb))) { qldpc_plan_destroy(p); return rc; }
-        std::vector<uint32_t> hc((size_t)n * t.mw, 0u);
-        for (int i = 0; i < m; ++i)
-            for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x) hc[(size_t)p->col_idx[x] * t.mw + (i >> 5)] |= 1u << (i & 31);
+        const int cwd = kColStride;
+        std::vector<uint32_t> hc((size_t)n * cwd, 0u);
+        if (t.mw <= 32)
+            for (int i = 0; i < m; ++i)
+                for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x) hc[(size_t)p->col_idx[x] * cwd + (i >> 5)] |= 1u << (i & 31);
         if ((rc = upload(&p->d_hcol, hc))) { qldpc_plan_destroy(p); return rc; }
         // GF(2) rank of H (gf2math.py:91-135) by bit-packed elimination on the host; OSD stops its column walk there
         std::vector<uint32_t> w(hb.begin(), hb.begin() + (size_t)m * t.nw);
@@ -554,11 +556,11 @@ int qldpc_plan_set_logicals(qldpc_plan *p, const uint32_t *rows, int32_t k)
     cudaFree(p->d_lcol);
     p->d_lcol = nullptr; p->logical_k = 0; p->lkw = 0;
     if (k == 0) return QLDPC_OK;
-    const int n = p->tab.n, nw = p->tab.nw, kw = (k + 31) / 32;
-    std::vector<uint32_t> cols((size_t)n * kw, 0u);
+    const int n = p->tab.n, nw = p->tab.nw, kw = (k + 31) / 32, cwd = kColStride;
+    std::vector<uint32_t> cols((size_t)n * cwd, 0u);
     for (int r = 0; r < k; ++r)
         for (int j = 0; j < n; ++j)
-            if ((rows[(size_t)r * nw + (j >> 5)] >> (j & 31)) & 1u) cols[(size_t)j * kw + (r >> 5)] |= 1u << (r & 31);
+            if ((rows[(size_t)r * nw + (j >> 5)] >> (j & 31)) & 1u) cols[(size_t)j * cwd + (r >> 5)] |= 1u << (r & 31);
     int rc = upload(&p->d_lcol, cols);
     if (rc) return rc;
     p->logical_k = k; p->lkw = kw;
@@ -801,14 +803,24 @@ int qldpc_classify(const qldpc_plan *px, const qldpc_plan *pz, const uint32_t *e
     a.hcol_z = px->d_hcol; a.hcol_x = pz->d_hcol;
     const bool lg = px->d_lcol && pz->d_lcol;
     a.lcol_z = lg ? px->d_lcol : nullptr; a.lcol_x = lg ? pz->d_lcol : nullptr;
-    a.kwz = px->lkw; a.kwx = pz->lkw;
     if (px->tab.mw > 32 || pz->tab.mw > 32) return fail(QLDPC_ETOOBIG, "classification supports up to 1024 checks per matrix");
     a.errx = errx; a.errz = errz; a.ehx = ehx; a.ehz = ehz; a.synz = synz; a.synx = synx; a.itx = itx; a.itz = itz;
     a.shots = shots;
     a.counters = reinterpret_cast<unsigned long long *>(counters);
     const int threads = 256;
     const int grid = (int)std::min<int64_t>((int64_t)px->sm_count * 8, (shots + 7) / 8);
-    classify_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(a);
+    // VH: 128-bit loads per column of H (both matrices use the wider one), VL: per column of the logical bases (2 or 8)
+    const int vh = col_words(std::max(px->tab.mw, pz->tab.mw)) / 4;
+    const bool wide = lg && (std::max(px->lkw, pz->lkw) > 8);
+    cudaStream_t cst = (cudaStream_t)stream;
+#define QLDPC_CLS(VH) do { if (wide) classify_kernel<VH, 8><<<grid, threads, 0, cst>>>(a); else classify_kernel<VH, 2><<<grid, threads, 0, cst>>>(a); } while (0)
+    switch (vh) {
+    case 1: QLDPC_CLS(1); break;
+    case 2: QLDPC_CLS(2); break;
+    case 4: QLDPC_CLS(4); break;
+    default: QLDPC_CLS(8); break;
+    }
+#undef QLDPC_CLS
     g_launches++;
     CU_TRY(cudaGetLastError());
     return QLDPC_OK;
