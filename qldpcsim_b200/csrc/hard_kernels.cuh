@@ -164,10 +164,9 @@ struct ClassifyArgs {
 // syndrome words, or null) and tested for zero.  cols: [n][kColStride] words (one 128-byte line per column, zero padded), of
 // which the first 4*V4 are read.
 template <int V4>
-__device__ __forceinline__ bool xor_columns_nonzero(const uint4 *__restrict__ cols, int nw, const uint32_t *x, const uint32_t *y,
-                                                    const uint32_t *init, int init_words, int lane)
+__device__ __forceinline__ void xor_columns(const uint4 *__restrict__ cols, int nw, const uint32_t *x, const uint32_t *y, int lane,
+                                            uint32_t acc[4 * V4])
 {
-    uint32_t acc[4 * V4];
 #pragma unroll
     for (int k = 0; k < 4 * V4; ++k) acc[k] = 0u;
     for (int w0 = 0; w0 < nw; w0 += 32) {
@@ -186,6 +185,14 @@ __device__ __forceinline__ bool xor_columns_nonzero(const uint4 *__restrict__ co
             }
         }
     }
+}
+
+template <int V4>
+__device__ __forceinline__ bool xor_columns_nonzero(const uint4 *__restrict__ cols, int nw, const uint32_t *x, const uint32_t *y,
+                                                    const uint32_t *init, int init_words, int lane)
+{
+    uint32_t acc[4 * V4];
+    xor_columns<V4>(cols, nw, x, y, lane, acc);
     bool bad = false;
 #pragma unroll
     for (int k = 0; k < 4 * V4; ++k) {

@@ -842,7 +842,16 @@ int qldpc_sample(const qldpc_plan *px, const qldpc_plan *pz, double prob, uint64
     const int threads = 256;
     const int grid = (int)std::min<int64_t>((int64_t)px->sm_count * 8, (shots + 7) / 8);
     const size_t smem = (size_t)(threads / 32) * 2 * a.gz.nw * 4;
-    sample_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+    a.hcol_z = px->d_hcol; a.hcol_x = pz->d_hcol;
+    const int mwmax = std::max(px->tab.mw, pz->tab.mw);
+    cudaStream_t cst = (cudaStream_t)stream;
+    if (mwmax > 32) sample_kernel<0><<<grid, threads, smem, cst>>>(a);
+    else switch (col_words(mwmax) / 4) {
+    case 1: sample_kernel<1><<<grid, threads, smem, cst>>>(a); break;
+    case 2: sample_kernel<2><<<grid, threads, smem, cst>>>(a); break;
+    case 4: sample_kernel<4><<<grid, threads, smem, cst>>>(a); break;
+    default: sample_kernel<8><<<grid, threads, smem, cst>>>(a); break;
+    }
     g_launches++;
     CU_TRY(cudaGetLastError());
     return QLDPC_OK;

@@ -19,6 +19,7 @@ struct SampleArgs {
     unsigned long long seed;
     long long first_shot, shots;
     uint32_t *errx, *errz, *synz, *synx;
+    const uint32_t *hcol_z, *hcol_x;       // [n][kColStride] bit-packed columns of Hz / Hx
 };
 
 __host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
@@ -48,6 +49,8 @@ __host__ __device__ inline void pauli_thresholds(double p, unsigned long long t[
     }
 }
 
+// VH: 128-bit loads per column of H (4*VH >= words(m) of both matrices); VH = 0: row-wise parities (more than 1024 checks)
+template <int VH>
 __global__ void __launch_bounds__(256) sample_kernel(SampleArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -60,43 +63,69 @@ __global__ void __launch_bounds__(256) sample_kernel(SampleArgs a)
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int nblk = (n + 3) / 4;                             // Philox blocks per shot: block b draws qubits 4b .. 4b+3
+    const int nblk_pad = (nw * 8 + 31) & ~31;                 // whole rounds of 32 blocks = 4 words
     for (long long s = warp_global; s < a.shots; s += nwarps) {
         const unsigned long long gs = (unsigned long long)(a.first_shot + s);
-        for (int w = lane; w < nw; w += 32) {
-            uint32_t wx = 0, wz = 0;
-#pragma unroll 2
-            for (int blk = 0; blk < 8; ++blk) {
+        // ---- draws: lane <-> block (all 32 lanes busy; a word is 8 consecutive blocks = 8 consecutive lanes, whose nibbles are
+        // OR-combined by three xor-shuffles)
+        for (int b0 = 0; b0 < nblk_pad; b0 += 32) {
+            const int b = b0 + lane;
+            uint32_t nx = 0, nz = 0;
+            if (b < nblk) {
                 uint32_t r[4];
-                philox4x32_10((uint32_t)gs, (uint32_t)(gs >> 32), (uint32_t)(w * 8 + blk), 0u, k0, k1, r);
+                philox4x32_10((uint32_t)gs, (uint32_t)(gs >> 32), (uint32_t)b, 0u, k0, k1, r);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const int bit = blk * 4 + q;
-                    if (w * 32 + bit < n) {
+                    if (4 * b + q < n) {
                         const unsigned long long x = r[q];
                         const bool X = x < thr[0], Y = (x >= thr[0]) && (x < thr[1]), Z = (x >= thr[1]) && (x < thr[2]);
-                        wx |= (uint32_t)(X || Y) << bit;
-                        wz |= (uint32_t)(Z || Y) << bit;
+                        nx |= (uint32_t)(X || Y) << q;
+                        nz |= (uint32_t)(Z || Y) << q;
                     }
                 }
             }
-            ex[w] = wx; ez[w] = wz;
-            a.errx[s * nw + w] = wx;
-            a.errz[s * nw + w] = wz;
+            uint32_t wx = nx << (4 * (lane & 7)), wz = nz << (4 * (lane & 7));
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+                wx |= __shfl_xor_sync(0xffffffffu, wx, d);
+                wz |= __shfl_xor_sync(0xffffffffu, wz, d);
+            }
+            const int w = b >> 3;
+            if ((lane & 7) == 0 && w < nw) {
+                ex[w] = wx; ez[w] = wz;
+                a.errx[s * nw + w] = wx;
+                a.errz[s * nw + w] = wz;
+            }
         }
         __syncwarp();
-        for (int w = 0; w < a.gz.mw; ++w) {                 // syn_z = Hz errX
-            const int i = w * 32 + lane;
-            uint32_t par = 0;
-            if (i < a.gz.m) for (int x = a.gz.row_ptr[i]; x < a.gz.row_ptr[i + 1]; ++x) par ^= get_bit(ex, a.gz.col_idx[x]);
-            const uint32_t bal = __ballot_sync(0xffffffffu, par);
-            if (lane == 0) a.synz[s * a.gz.mw + w] = bal;
-        }
-        for (int w = 0; w < a.gx.mw; ++w) {                 // syn_x = Hx errZ
-            const int i = w * 32 + lane;
-            uint32_t par = 0;
-            if (i < a.gx.m) for (int x = a.gx.row_ptr[i]; x < a.gx.row_ptr[i + 1]; ++x) par ^= get_bit(ez, a.gx.col_idx[x]);
-            const uint32_t bal = __ballot_sync(0xffffffffu, par);
-            if (lane == 0) a.synx[s * a.gx.mw + w] = bal;
+        // ---- syndromes: syn_z = Hz errX, syn_x = Hx errZ as XORs of the bit-packed columns selected by the (sparse) errors
+        if (VH > 0) {
+            constexpr int V = VH > 0 ? VH : 1;
+            uint32_t sz[4 * V], sx[4 * V];
+            xor_columns<V>(reinterpret_cast<const uint4 *>(a.hcol_z), nw, ex, nullptr, lane, sz);
+            xor_columns<V>(reinterpret_cast<const uint4 *>(a.hcol_x), nw, ez, nullptr, lane, sx);
+#pragma unroll
+            for (int k = 0; k < 4 * V; ++k) {
+                const uint32_t rz = __reduce_xor_sync(0xffffffffu, sz[k]), rx = __reduce_xor_sync(0xffffffffu, sx[k]);
+                if (lane == 0 && k < a.gz.mw) a.synz[s * a.gz.mw + k] = rz;
+                if (lane == 0 && k < a.gx.mw) a.synx[s * a.gx.mw + k] = rx;
+            }
+        } else {
+            for (int w = 0; w < a.gz.mw; ++w) {                 // more than 1024 checks: row-wise parities
+                const int i = w * 32 + lane;
+                uint32_t par = 0;
+                if (i < a.gz.m) for (int x = a.gz.row_ptr[i]; x < a.gz.row_ptr[i + 1]; ++x) par ^= get_bit(ex, a.gz.col_idx[x]);
+                const uint32_t bal = __ballot_sync(0xffffffffu, par);
+                if (lane == 0) a.synz[s * a.gz.mw + w] = bal;
+            }
+            for (int w = 0; w < a.gx.mw; ++w) {
+                const int i = w * 32 + lane;
+                uint32_t par = 0;
+                if (i < a.gx.m) for (int x = a.gx.row_ptr[i]; x < a.gx.row_ptr[i + 1]; ++x) par ^= get_bit(ez, a.gx.col_idx[x]);
+                const uint32_t bal = __ballot_sync(0xffffffffu, par);
+                if (lane == 0) a.synx[s * a.gx.mw + w] = bal;
+            }
         }
         __syncwarp();
     }
