@@ -58,7 +58,8 @@ struct MsTables {
     int c2v_words;       // words of the per-shot c2v array (multiple of 32: every region starts on bank 0)
     int off_chk;         // u32 [dc*ms]   lo16 = 4*j' (byte offset of S_j'), hi16 = byte offset of the edge's c2v word; kMsPad past a short row
     int off_layer;       // u16 [nl][8]   16-byte record per layer: {qb, qe (range in layer_chk), lanes per check (1, 2, 4 or 8),
-                         //               vb, ve (range in lvar, 32-bit entries, multiples of 32), 0, 0, 0}
+                         //               vb, ve (range in lvar, 32-bit entries, multiples of 32), 1 if the second sub-group of the
+                         //               layer's LAST pair-trip is empty (a single-variable trip is run instead), 0, 0}
     int off_layer_chk;   // u16 [...]     check indices, layer by layer
     int off_lvar;        // u32 [...]     lo16 = 4*j'_a, hi16 = 4*j'_b: the two variables of (trip, lane); dummy = 4*n
     int off_col_ptr;     // u16 [n+2]     CSC pointers in the renumbering (variable n: empty)
@@ -247,6 +248,18 @@ __device__ __forceinline__ void ms_var_update2(uint32_t ja4, uint32_t jb4, int l
     }
 }
 
+// Single variable per lane: layers that touch at most 32 variables (single-check layers of the serial schedule, bicycle).
+template <int DV, int DMIN>
+__device__ __forceinline__ void ms_var_update1(uint32_t ja4, int lane, const MsAddr &A, const MsTables &t, float Tf, int &delta)
+{
+    const uint32_t sa = A.S + ja4;
+    const float a_old = sld_f32(sa);
+    const float a = ms_colsum<DV, DMIN>(A.c2v + ja4, ja4, t);
+    sst_f32(sa, a);
+    const uint32_t fa = __ballot_sync(0xffffffffu, (a < Tf) != (a_old < Tf));   // hard decision flipped (:173-174)
+    if (fa) ms_apply_flips(fa, ja4, lane, A, delta);
+}
+
 // Same with FOUR variables per lane (two consecutive pair-trips of the layer's list at once): more independent chains in
 // flight and half the loop overhead for the common layers whose variables fill four sub-groups.
 template <int DV, int DMIN>
@@ -368,7 +381,8 @@ __global__ void __launch_bounds__(kMsMaxWarps * 32, 1) ms_decode_kernel(MsTables
                     ms_var_update4<DV, DMIN>(sld_u32(lvar + 4u * q), sld_u32(lvar + 4u * q + 128u), lane, A, t, Tf, delta);
                 if (q < ve) {
                     const uint32_t e = sld_u32(lvar + 4u * q);
-                    ms_var_update2<DV, DMIN>(e & 0xffffu, e >> 16, lane, A, t, Tf, delta);
+                    if (r2 >> 16) ms_var_update1<DV, DMIN>(e & 0xffffu, lane, A, t, Tf, delta);      // last pair-trip holds one sub-group only
+                    else ms_var_update2<DV, DMIN>(e & 0xffffu, e >> 16, lane, A, t, Tf, delta);
                 }
                 unsat += __reduce_add_sync(full, delta);
                 __syncwarp();

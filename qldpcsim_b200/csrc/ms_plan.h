@@ -138,7 +138,9 @@ struct Evaluator {
         }
         std::sort(vs.begin(), vs.end());
         vs.erase(std::unique(vs.begin(), vs.end()), vs.end());
-        const int V = (int)vs.size(), G = 2 * ((V + 63) / 64);
+        // as few sub-groups as possible (an instruction stream per sub-group costs more than a two-way bank conflict); the list
+        // is padded to whole pair-trips with an empty sub-group, which the kernel skips (single-variable trip)
+        const int V = (int)vs.size(), Gfill = (V + 31) / 32, G = (Gfill + 1) & ~1;
         std::vector<std::vector<int>> sub(G);
         std::vector<int> res_cnt((size_t)G * 32, 0);
         std::vector<std::vector<int>> by_res(32);
@@ -148,8 +150,8 @@ struct Evaluator {
         // it take second, third ... members of the largest classes.  Unavoidable conflicts thus end up concentrated in few
         // sub-groups instead of being spread over all of them.
         int remaining = V;
-        for (int g2 = 0; g2 < G; ++g2) {
-            const int need = std::min(32, std::max(0, remaining - 32 * (G - g2 - 1)));
+        for (int g2 = 0; g2 < Gfill; ++g2) {
+            const int need = std::min(32, std::max(0, remaining - 32 * (Gfill - g2 - 1)));
             int taken = 0;
             for (int round = 0; round < 32 && (round == 0 || taken < need); ++round) {
                 int rs[32];
@@ -168,7 +170,7 @@ struct Evaluator {
         }
         long long cost = 0;
         const int per = 2 + L.dv_inst;
-        for (int g2 = 0; g2 < G; ++g2) {
+        for (int g2 = 0; g2 < Gfill; ++g2) {
             int mx = 0;
             for (int r = 0; r < 32; ++r) mx = std::max(mx, res_cnt[(size_t)g2 * 32 + r]);
             cost += (long long)per * std::max(mx, 1);

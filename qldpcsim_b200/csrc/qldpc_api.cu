@@ -324,6 +324,9 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
                 uint16_t *r = &b[mt.off_layer + 8 * l];
                 r[0] = (uint16_t)p->layer_ptr[l]; r[1] = (uint16_t)p->layer_ptr[l + 1]; r[2] = (uint16_t)pl.lpc[l];
                 r[3] = (uint16_t)pl.lvar_ptr[l]; r[4] = (uint16_t)pl.lvar_ptr[l + 1];
+                bool single = pl.lvar_ptr[l + 1] > pl.lvar_ptr[l];
+                for (int x = pl.lvar_ptr[l + 1] - 32; single && x < pl.lvar_ptr[l + 1]; ++x) single = (pl.lvar[x] >> 16) == 4u * (uint32_t)n;
+                r[5] = single ? 1 : 0;
             }
             mt.off_layer_chk = put((int)p->layer_chk.size());
             for (size_t x = 0; x < p->layer_chk.size(); ++x) b[mt.off_layer_chk + x] = (uint16_t)p->layer_chk[x];
