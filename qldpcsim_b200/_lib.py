@@ -9,7 +9,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libqldpc_b200.so")
+LIB_PATH = os.environ.get("QLDPC_B200_LIB") or os.path.join(HERE, "libqldpc_b200.so")     # override: experiments only
 
 NG, BF, MS, BP = 0, 1, 2, 3
 DEC_TYPES = {"NG": NG, "BF": BF, "MS": MS, "BP": BP}

@@ -17,7 +17,8 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not f.endswith("codes.npz"))
+    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
+                  if not f.endswith("codes.npz") and not os.path.basename(f).startswith("big_"))
 
 
 def load_golden(name):

@@ -345,3 +345,26 @@ def test_outcome_classes(code, decType, sched, p, shots, cuda_device):
     assert got["outcome_logical_error"] == want["logical_error"]
     assert got["outcome_decoder_failure"] == want["decoder_failure"]
     assert sum(want.values()) == shots
+
+
+def test_bp_big_reference_golden(cuda_device):
+    """GPU sum-product decoder against 1600 decodes of the unmodified reference (see tests/golden/make_bp_golden.py and the
+    CPU twin of this test in test_oracle_golden.py for why the bar on this configuration is 99.5 % and not 99.9 %)."""
+    import os
+    from conftest import GOLDEN_DIR
+    from qldpcsim_b200 import bitpack, pcm, pcmlibrary
+    from qldpcsim_b200.decoders import Decoder
+    g = np.load(os.path.join(GOLDEN_DIR, "big_LP118_0_BP_F_p05_X.npz"))
+    Hx, Hz = [(h % 2).astype(np.int8) for h in pcmlibrary.by_name("LP118_0")]
+    m, n = Hz.shape
+    syn = bitpack.unpack_rows(g["syn"], m).astype(np.uint8)
+    e_ref, it_ref, iters = bitpack.unpack_rows(g["e"], n), g["it"], int(g["decIterations"])
+    lX, _ = pcm.schedule_layers(Hx, Hz, "F")
+    out = Decoder(Hz, "BP", p=float(g["p"]) / 3, max_iter=iters, layers=lX).decode(syn)
+    same = (out["e_hat"] == e_ref).all(1) & (out["iters"] == it_ref)
+    assert same.mean() >= 0.995, same.mean()
+    assert same[it_ref <= 20].all()
+    shots = len(it_ref)
+    f_ref = float(((e_ref.astype(np.int64) @ Hz.T.astype(np.int64)) % 2 != syn).any(1).mean())
+    f_gpu = float(((out["e_hat"].astype(np.int64) @ Hz.T.astype(np.int64)) % 2 != syn).any(1).mean())
+    assert abs(f_gpu - f_ref) <= 1.96 * np.sqrt(f_ref * (1 - f_ref) / shots) + 1.0 / shots

@@ -87,3 +87,28 @@ def test_survey_golden_table():
             "LP04_0_BF_p02": (59, 59, 20, 0, 3334, 3089)}
     for name, c in want.items():
         assert tuple(load_golden(name)["counters"]) == c, name
+
+
+def test_bp_big_reference_golden_documents_the_reachable_bar():
+    """1600 LP118_0 BP decodes of the unmodified reference (tests/golden/make_bp_golden.py).  The oracle uses glibc's tanh /
+    atanh, the reference NumPy's SIMD routines: decodes that converge agree to the bit, decodes that never converge are
+    chaotic in the last bit of those functions.  Measured: 99.69 % overall -- the north star's 99.9 % is not reachable on
+    this configuration without NumPy's own tanh; what is asserted is >= 99.5 %, every quickly converging decode identical,
+    and a failure rate inside the reference's 95 % binomial interval."""
+    import os
+    from conftest import GOLDEN_DIR
+    from qldpcsim_b200 import bitpack, pcm, pcmlibrary
+    g = np.load(os.path.join(GOLDEN_DIR, "big_LP118_0_BP_F_p05_X.npz"))
+    Hx, Hz = [(h % 2).astype(np.int8) for h in pcmlibrary.by_name("LP118_0")]
+    m, n = Hz.shape
+    syn = bitpack.unpack_rows(g["syn"], m).astype(np.uint8)
+    e_ref, it_ref, iters = bitpack.unpack_rows(g["e"], n), g["it"], int(g["decIterations"])
+    lX, _ = pcm.schedule_layers(Hx, Hz, "F")
+    o = oracle.Graph(Hz).decode("BP", syn, p=float(g["p"]) / 3, max_iter=iters, layers=lX)
+    same = (o["e_hat"] == e_ref).all(1) & (o["iters"] == it_ref)
+    assert same.mean() >= 0.995
+    assert same[it_ref <= 20].all()
+    shots = len(it_ref)
+    f_ref = float(((e_ref.astype(np.int64) @ Hz.T.astype(np.int64)) % 2 != syn).any(1).mean())
+    f_orc = float(((o["e_hat"].astype(np.int64) @ Hz.T.astype(np.int64)) % 2 != syn).any(1).mean())
+    assert abs(f_orc - f_ref) <= 1.96 * np.sqrt(f_ref * (1 - f_ref) / shots) + 1.0 / shots
