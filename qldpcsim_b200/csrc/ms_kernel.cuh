@@ -43,7 +43,6 @@ namespace qldpc {
 
 constexpr int kMsMaxWarps = 24;   // 768 threads per CTA -> up to 85 registers per thread
 constexpr int kMsMaxDv = 16;
-constexpr uint32_t kMsPad = 0xFFFFFFFFu;   // padding entry of the check table (short rows)
 
 // Device view of the min-sum tables.  One uint16 blob per plan, copied to shared memory once per CTA; offsets are
 // in uint16 units (32-bit tables start on even offsets).  j' = renumbered variable (descending column weight).
@@ -56,7 +55,8 @@ struct MsTables {
     int ms;              // row stride of chk (>= m; ms = 4 mod 8 keeps the lane groups of a split check on disjoint banks)
     int n_pad;           // n rounded up to a multiple of 64 (first-step sweep: two variables per lane and trip)
     int c2v_words;       // words of the per-shot c2v array (multiple of 32: every region starts on bank 0)
-    int off_chk;         // u32 [dc*ms]   lo16 = 4*j' (byte offset of S_j'), hi16 = byte offset of the edge's c2v word; kMsPad past a short row
+    int off_chk;         // u32 [dc*ms]   lo16 = 4*j' (byte offset of S_j'), hi16 = byte offset of the edge's c2v word.  Slots past the
+                         //               end of a short row hold a PADDING EDGE: S entry n+1 (always +inf) and the scratch word S[n+2]
     int off_layer;       // u16 [nl][8]   16-byte record per layer: {qb, qe (range in layer_chk), lanes per check (1, 2, 4 or 8),
                          //               vb, ve (range in lvar, 32-bit entries, multiples of 32), 1 if the second sub-group of the
                          //               layer's LAST pair-trip is empty (a single-variable trip is run instead), 0, 0}
@@ -74,7 +74,9 @@ struct MsTables {
 struct MsSmemLayout {
     // per-shot state, offsets in bytes from the warp's base; c2v and S are contiguous (one zero fill)
     int off_c2v;   // float [c2v_words]
-    int off_S;     // float [n + 1] (entry n: dummy variable of the padded lists) rounded up to 4 words
+    int off_S;     // float [n + 3] rounded up to 4 words: entry n = dummy variable of the padded lists, entry n+1 = +inf (the
+                   // "posterior" of a padding edge: its |b| is +inf, so it never wins a minimum and its sign is +), entry n+2 =
+                   // scratch c2v word of the padding edges
     int off_par;   // uint32 [mw]
     int off_syn;   // uint32 [mw]
     int zero_words;
@@ -86,7 +88,7 @@ __host__ __device__ inline MsSmemLayout ms_layout(const MsTables &t)
     MsSmemLayout l;
     int o = 0;
     l.off_c2v = o; o += 4 * t.c2v_words;
-    l.off_S = o;   o += 4 * ((t.n + 1 + 3) & ~3);
+    l.off_S = o;   o += 4 * ((t.n + 3 + 3) & ~3);
     l.zero_words = o / 4;
     l.off_par = o; o += 4 * t.mw;
     l.off_syn = o; o += 4 * t.mw;
@@ -124,12 +126,12 @@ struct MsAddr {          // shared-window byte addresses, warp-uniform
 // the edges within a check is free), and the min / second-min / merge logic is binary32 FMNMX instead of binary64
 // compare+select chains.  The sign of b_k is the sign of v2c_k (v2c is never -0.0: it is a difference whose minuend is never
 // -0.0, and rounding keeps signs).  beta < 0: the caller passes |beta| and folds the extra sign into `sgn_extra`.
-template <int DC, bool REGULAR, int LPC>
+template <int DC, int LPC>
 __device__ __forceinline__ void ms_check_phase(int qb, int qe, int lane, const MsAddr &A, double prior, double beta, uint32_t sgn_extra)
 {
-    constexpr int SPL = (DC + LPC - 1) / LPC;       // slots per lane
+    static_assert(DC % LPC == 0, "row-weight classes are multiples of the lane split");
+    constexpr int SPL = DC / LPC;                   // slots per lane
     constexpr int CPP = 32 / LPC;                   // checks per pass
-    constexpr bool EXACT = (LPC * SPL == DC);       // no lane owns a slot >= DC
     const int h = lane % LPC;                       // which slice of the row
     const int k0 = h * SPL;                         // first slot of the lane
     const float inf = __int_as_float(0x7f800000);
@@ -139,27 +141,21 @@ __device__ __forceinline__ void ms_check_phase(int qb, int qe, int lane, const M
         const uint32_t i = sld_u16(A.layer_chk + 2u * (uint32_t)(act ? q : qb));
         const uint32_t ct = A.chk + (uint32_t)k0 * A.m4 + 4u * i;        // &chk[k0*ms + i]
         float bs[SPL];                              // signed b_k of the lane's own slots
-        uint32_t ca[SPL];                           // shared address of the slot's c2v word (0 = padding)
+        uint32_t ca[SPL];                           // shared address of the slot's c2v word
         float m1 = inf, m2 = inf;                   // smallest / second smallest |b| (inf if none)
         uint32_t px = 0;                            // xor of the b_k bit patterns: bit 31 = parity of the negative signs
 #pragma unroll
         for (int s = 0; s < SPL; ++s) {
-            bs[s] = 0.0f;
-            ca[s] = 0u;
-            if (EXACT || k0 + s < DC) {
-                const uint32_t e = sld_u32(ct + (uint32_t)s * A.m4);
-                if (REGULAR || e != kMsPad) {
-                    ca[s] = A.c2v + (e >> 16);
-                    const double post = __dadd_rn(prior, (double)sld_f32(A.S + (e & 0xffffu)));          // :173
-                    const double v = __dsub_rn(post, (double)sld_f32(ca[s]));                            // :177
-                    const float b = __double2float_rn(__dmul_rn(beta, v));                               // :167-168 (f64 product, f32 store)
-                    bs[s] = b;
-                    px ^= __float_as_uint(b);                                                             // :157-159
-                    const float ab = fabsf(b);
-                    m2 = fminf(m2, fmaxf(m1, ab));                                                        // :162-164
-                    m1 = fminf(m1, ab);                                                                   // :160
-                }
-            }
+            const uint32_t e = sld_u32(ct + (uint32_t)s * A.m4);
+            ca[s] = A.c2v + (e >> 16);
+            const double post = __dadd_rn(prior, (double)sld_f32(A.S + (e & 0xffffu)));          // :173
+            const double v = __dsub_rn(post, (double)sld_f32(ca[s]));                            // :177
+            const float b = __double2float_rn(__dmul_rn(beta, v));                               // :167-168 (f64 product, f32 store)
+            bs[s] = b;
+            px ^= __float_as_uint(b);                                                             // :157-159
+            const float ab = fabsf(b);
+            m2 = fminf(m2, fmaxf(m1, ab));                                                        // :162-164
+            m1 = fminf(m1, ab);                                                                   // :160
         }
         // butterfly over the LPC lanes of the check
 #pragma unroll
@@ -179,12 +175,8 @@ __device__ __forceinline__ void ms_check_phase(int qb, int qe, int lane, const M
             const uint32_t r1s = __float_as_uint(r1) | P, r2s = __float_as_uint(r2) | P;
 #pragma unroll
             for (int s = 0; s < SPL; ++s) {
-                if (EXACT || k0 + s < DC) {
-                    if (REGULAR || ca[s] != 0u) {
-                        const uint32_t mag = (fabsf(bs[s]) == m1) ? r2s : r1s;
-                        sst_u32(ca[s], mag ^ (__float_as_uint(bs[s]) & 0x80000000u));
-                    }
-                }
+                const uint32_t mag = (fabsf(bs[s]) == m1) ? r2s : r1s;
+                sst_u32(ca[s], mag ^ (__float_as_uint(bs[s]) & 0x80000000u));
             }
         }
     }
@@ -283,9 +275,9 @@ __device__ __forceinline__ void ms_var_update4(uint32_t e0, uint32_t e1, int lan
     }
 }
 
-// DC: instantiated row weight, REGULAR: every row has exactly DC edges, DV: instantiated column weight, DMIN: number of
+// DC: instantiated row weight (shorter rows are filled with padding edges), DV: instantiated column weight, DMIN: number of
 // leading regions that hold every variable (0 = guard all).
-template <int DC, bool REGULAR, int DV, int DMIN>
+template <int DC, int DV, int DMIN>
 __global__ void __launch_bounds__(kMsMaxWarps * 32, 1) ms_decode_kernel(MsTables t, const uint16_t *__restrict__ blob, MsConst c, DecodeIO io)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -334,6 +326,8 @@ __global__ void __launch_bounds__(kMsMaxWarps * 32, 1) ms_decode_kernel(MsTables
         // ---- initial state: c2v = 0 (decoders.py:150), S = 0, residual = syndrome (+ H.1 if the all-zero sums decide 1)
         for (int i = lane * 4; i < lay.zero_words; i += 128)
             asm volatile("st.shared.v4.f32 [%0], {%1,%1,%1,%1};" :: "r"(A.c2v + 4u * i), "f"(0.0f) : "memory");
+        __syncwarp();
+        if (lane == 0) sst_u32(A.S + n4 + 4u, 0x7f800000u);            // S[n+1] = +inf: the padding edges
         int unsat = 0;
         for (int i = lane; i < t.mw; i += 32) {
             const uint32_t w = io.syn[shot * t.mw + i];
@@ -352,7 +346,7 @@ __global__ void __launch_bounds__(kMsMaxWarps * 32, 1) ms_decode_kernel(MsTables
             // phase visits EVERY variable (the reference recomputes all posteriors; a variable outside layer 0 has
             // posterior L, which may be negative for p > 1/2)
             const int qb = sld_u16(layer_rec), qe = sld_u16(layer_rec + 2u);
-            ms_check_phase<DC, REGULAR, 1>(qb, qe, lane, A, c.Lf, c.abeta, c.sgn);
+            ms_check_phase<DC, 1>(qb, qe, lane, A, c.Lf, c.abeta, c.sgn);
             __syncwarp();
             int delta = 0;
             for (int q = lane; q < t.n_pad; q += 64)
@@ -367,10 +361,10 @@ __global__ void __launch_bounds__(kMsMaxWarps * 32, 1) ms_decode_kernel(MsTables
                 uint32_t r0, r1, r2, r3;                                       // the layer's 16-byte record
                 asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(layer_rec + 16u * l));
                 const int qb = r0 & 0xffffu, qe = r0 >> 16, lpc = r1 & 0xffffu;
-                if (lpc == 1) ms_check_phase<DC, REGULAR, 1>(qb, qe, lane, A, c.L, c.abeta, c.sgn);
-                else if (lpc == 2) ms_check_phase<DC, REGULAR, 2>(qb, qe, lane, A, c.L, c.abeta, c.sgn);
-                else if (lpc == 4) ms_check_phase<DC, REGULAR, 4>(qb, qe, lane, A, c.L, c.abeta, c.sgn);
-                else ms_check_phase<DC, REGULAR, 8>(qb, qe, lane, A, c.L, c.abeta, c.sgn);
+                if (lpc == 1) ms_check_phase<DC, 1>(qb, qe, lane, A, c.L, c.abeta, c.sgn);
+                else if (lpc == 2) ms_check_phase<DC, 2>(qb, qe, lane, A, c.L, c.abeta, c.sgn);
+                else if (lpc == 4) ms_check_phase<DC, 4>(qb, qe, lane, A, c.L, c.abeta, c.sgn);
+                else if constexpr (DC % 8 == 0) ms_check_phase<DC, 8>(qb, qe, lane, A, c.L, c.abeta, c.sgn);   // DC = 4: lpc <= 4
                 __syncwarp();
                 // ---------------- variable-node phase (decoders.py:172-174) on the variables whose sums changed.  Every
                 // lane runs the same number of trips (lists are padded to whole trips with the dummy variable n).

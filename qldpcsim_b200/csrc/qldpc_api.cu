@@ -67,47 +67,42 @@ GraphDev graph_dev(const qldpc_plan *p)
 // ---- min-sum kernel dispatch on (row weight, regular rows, column weight, unguarded regions)
 typedef void (*ms_kernel_t)(MsTables, const uint16_t *, MsConst, DecodeIO);
 
-template <int DC, int DV, int DMIN>
-ms_kernel_t ms_pick(bool regular)
-{
-    return regular ? (ms_kernel_t)ms_decode_kernel<DC, true, DV, DMIN> : (ms_kernel_t)ms_decode_kernel<DC, false, DV, DMIN>;
-}
-
 // DMIN is either 0 (every region guarded by the degree test) or the fast value of the shape: 3 for column weights <= 5
 // (the lifted-product / Tanner codes have column weights 3..5), DV for the others (column-regular codes such as bicycle).
 constexpr int ms_fast_dmin(int dv_inst) { return dv_inst <= 5 ? 3 : (dv_inst <= 9 ? dv_inst : 0); }
 
 template <int DC>
-ms_kernel_t ms_pick_dv(int dv_inst, bool fast, bool regular)
+ms_kernel_t ms_pick_dv(int dv_inst, bool fast)
 {
     switch (dv_inst) {
-    case 4: return fast ? ms_pick<DC, 4, ms_fast_dmin(4)>(regular) : ms_pick<DC, 4, 0>(regular);
-    case 5: return fast ? ms_pick<DC, 5, ms_fast_dmin(5)>(regular) : ms_pick<DC, 5, 0>(regular);
-    case 9: return fast ? ms_pick<DC, 9, ms_fast_dmin(9)>(regular) : ms_pick<DC, 9, 0>(regular);
-    case 16: return ms_pick<DC, 16, 0>(regular);
+    case 4: return fast ? (ms_kernel_t)ms_decode_kernel<DC, 4, ms_fast_dmin(4)> : (ms_kernel_t)ms_decode_kernel<DC, 4, 0>;
+    case 5: return fast ? (ms_kernel_t)ms_decode_kernel<DC, 5, ms_fast_dmin(5)> : (ms_kernel_t)ms_decode_kernel<DC, 5, 0>;
+    case 9: return fast ? (ms_kernel_t)ms_decode_kernel<DC, 9, ms_fast_dmin(9)> : (ms_kernel_t)ms_decode_kernel<DC, 9, 0>;
+    case 16: return (ms_kernel_t)ms_decode_kernel<DC, 16, 0>;
     }
     return nullptr;
 }
 
-// Instantiated shapes: row weight <= 4 / 8 / 18 / 32, column weight <= 4 / 5 / 9 / 16.  `full_regions` = number of leading
-// regions that hold every variable; *dmin receives the DMIN of the chosen kernel.
-ms_kernel_t ms_select(int dc, int dv, bool regular, int full_regions, int *dc_inst, int *dv_inst, int *dmin)
+// Instantiated shapes: row weight <= 4 / 8 / 16 / 24 / 32 (multiples of every lane split; shorter rows get padding edges),
+// column weight <= 4 / 5 / 9 / 16.  `full_regions` = number of leading regions that hold every variable; *dmin receives the
+// DMIN of the chosen kernel.
+ms_kernel_t ms_select(int dc, int dv, int full_regions, int *dc_inst, int *dv_inst, int *dmin)
 {
-    static const int dcs[] = {4, 8, 18, 32}, dvs[] = {4, 5, 9, 16};
+    static const int dcs[] = {4, 8, 16, 24, 32}, dvs[] = {4, 5, 9, 16};
     int pc = 0, pv = 0;
     for (int s : dcs) if (!pc && s >= dc) pc = s;
     for (int s : dvs) if (!pv && s >= dv) pv = s;
     *dc_inst = pc; *dv_inst = pv; *dmin = 0;
     if (!pc || !pv) return nullptr;
-    const bool reg = regular && pc == dc;
     const int fd = ms_fast_dmin(pv);
     const bool fast = fd > 0 && full_regions >= fd;
     *dmin = fast ? fd : 0;
     switch (pc) {
-    case 4: return ms_pick_dv<4>(pv, fast, reg);
-    case 8: return ms_pick_dv<8>(pv, fast, reg);
-    case 18: return ms_pick_dv<18>(pv, fast, reg);
-    case 32: return ms_pick_dv<32>(pv, fast, reg);
+    case 4: return ms_pick_dv<4>(pv, fast);
+    case 8: return ms_pick_dv<8>(pv, fast);
+    case 16: return ms_pick_dv<16>(pv, fast);
+    case 24: return ms_pick_dv<24>(pv, fast);
+    case 32: return ms_pick_dv<32>(pv, fast);
     }
     return nullptr;
 }
@@ -291,7 +286,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
                 full_regions = std::min(dmin_true, dv);
             }
             int dc_inst = 0, dv_inst = 0, dmin = 0;
-            pk->ms = ms_select(dc, dv, regular, full_regions, &dc_inst, &dv_inst, &dmin);
+            pk->ms = ms_select(dc, dv, full_regions, &dc_inst, &dv_inst, &dmin);
             if (!pk->ms) return bail(QLDPC_ETOOBIG, "min-sum kernels are instantiated for row weight <= 32 and column weight <= 16");
             MsGraphView gv{m, n, E, p->row_ptr.data(), p->col_idx.data(), p->col_ptr.data(), p->row_idx.data(), nl, p->layer_ptr.data(), p->layer_chk.data()};
             MsPlanLayout pl;
@@ -301,7 +296,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             mt.n_pad = (n + 63) & ~63;
             for (int x = 0; x < kMsMaxDv; ++x) { mt.cnt4[x] = 4 * pl.cnt[x]; mt.coff4[x] = 4 * pl.coff[x]; }
             mt.c2v_words = pl.c2v_words;
-            if (4ll * mt.c2v_words > 65535 || 4ll * (n + 1) > 65535)
+            if (4ll * mt.c2v_words + 4ll * (n + 3) > 65535)
                 return bail(QLDPC_ETOOBIG, "code too large for the 16-bit shared-memory offset tables (need 4*edges < 65536, 4*n < 65536)");
             // slot stride: with LPC lanes per check, lane h starts at slot h*SPL, i.e. SPL*ms words further; ms = 4 (mod 8)
             // puts the lane groups of a split check on disjoint banks
@@ -309,7 +304,9 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             while (ms % 8 != 4) ++ms;
             mt.ms = ms;
             mt.off_chk = put32(dc_inst * ms);
-            for (int x = 0; x < dc_inst * ms; ++x) set32(mt.off_chk, x, kMsPad);
+            // padding edge: S entry n+1 (+inf) and the scratch word S[n+2], addressed relative to the c2v array like every c2v word
+            const uint32_t pad_edge = (uint32_t)(4 * (n + 1)) | ((uint32_t)(4 * mt.c2v_words + 4 * (n + 2)) << 16);
+            for (int x = 0; x < dc_inst * ms; ++x) set32(mt.off_chk, x, pad_edge);
             for (int i = 0; i < m; ++i)
                 for (int k = 0; k < dc_inst; ++k) {
                     const int e = pl.slot_edge[(size_t)i * dc_inst + k];
