@@ -159,3 +159,23 @@ def test_no_cpu_fallback():
         decoders.NG_decoder(H, np.zeros(3, int))
     with pytest.raises(_lib.QldpcError):
         decoders.Decoder(H, "MS", p=0.01, layers=[np.arange(3)])
+
+
+@pytest.mark.parametrize("code,k", [("steane", 1), ("shor", 1), ("LP04_0", 19), ("LP118_0", 80), ("bicycle", 36)])
+def test_logical_operators(code, k):
+    """Bases of the logical operators used by the true outcome classes (extension, README.md:15-22): k = n - rank(Hx) - rank(Hz)
+    operators of each type, commuting with the stabilisers of the other type, independent of the stabilisers of their own type,
+    and pairing non-degenerately with each other."""
+    Hx, Hz = [(h % 2).astype(np.int64) for h in pcmlibrary.by_name(code)]
+    Lx, Lz = pcm.logical_operators(Hx, Hz)
+    assert Lx.shape == (k, Hx.shape[1]) and Lz.shape == (k, Hx.shape[1])
+    assert not ((Hz @ Lx.T) % 2).any() and not ((Hx @ Lz.T) % 2).any()
+
+    def rank(M):
+        span = pcm._GF2Span()
+        return sum(span.add(v) for v in pcm._rows_to_ints(M))
+    assert rank(np.vstack([Hx, Lx])) == rank(Hx) + k and rank(np.vstack([Hz, Lz])) == rank(Hz) + k
+    assert rank((Lx @ Lz.T) % 2) == k
+    # null space: every basis vector is annihilated, dimension n - rank
+    N = pcm._ints_to_rows(pcm.gf2_nullspace(Hz), Hz.shape[1]).astype(np.int64)
+    assert not ((Hz @ N.T) % 2).any() and N.shape[0] == Hz.shape[1] - rank(Hz)
