@@ -357,68 +357,85 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             fn = (const void *)pk->ms;
         } else {
             // ================= sum-product tables (slot-major edge layout, see common.cuh) =================
-            // slot stride = m: padding it to spread the slots of a check over the banks was measured SLOWER (LP118_0: one
-            // shot fewer per SM, 4.04e10 vs 4.26e10 edge-iterations/s) -- the kernel is bound by the binary64 tanh / atanh
-            // instruction streams and by occupancy, not by shared-memory wavefronts
-            const int ms = m;
-            t.ms = ms;
-            if ((long long)dc * ms > 65535) return bail(QLDPC_ETOOBIG, "code too large for the on-chip decoder tables (need m*row_weight <= 65535, n < 65535, row weight <= 32)");
-            t.off_var = put(dc * ms);
-            std::fill(b.begin() + t.off_var, b.begin() + t.off_var + dc * ms, kPad);
-            for (int i = 0; i < m; ++i)
-                for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x) b[t.off_var + (x - p->row_ptr[i]) * ms + i] = (uint16_t)(4 * p->col_idx[x]);
-            t.off_col_ptr = put(n + 1);
-            for (int j = 0; j <= n; ++j) b[t.off_col_ptr + j] = (uint16_t)p->col_ptr[j];
-            t.off_col_pos = put(E);
-            t.off_col_chk = put(E);
-            for (int x = 0; x < E; ++x) {
-                b[t.off_col_pos + x] = (uint16_t)(col_slot[x] * ms + p->row_idx[x]);
-                b[t.off_col_chk + x] = (uint16_t)p->row_idx[x];
-            }
-            t.dvs = 0;
-            t.off_vn = 0;
-            t.n_pad = (n + 31) & ~31;
-            t.off_rowpar = put(2 * t.mw);
-            for (int i = 0; i < m; ++i)
-                if ((p->row_ptr[i + 1] - p->row_ptr[i]) & 1) b[t.off_rowpar + 2 * (i >> 5) + ((i & 31) >> 4)] |= (uint16_t)(1u << (i & 15));
-            t.off_layer_lpc = put(nl);
-            t.off_layer_ptr = put(nl + 1);
-            for (int l = 0; l <= nl; ++l) b[t.off_layer_ptr + l] = (uint16_t)p->layer_ptr[l];
-            t.off_layer_chk = put((int)p->layer_chk.size());
-            for (size_t x = 0; x < p->layer_chk.size(); ++x) b[t.off_layer_chk + x] = (uint16_t)p->layer_chk[x];
-            std::vector<int> lvar_ptr(nl + 1, 0);
-            std::vector<uint16_t> lvar;
-            for (int l = 0; l < nl; ++l) {
-                for (int v : layer_vars(l)) lvar.push_back((uint16_t)v);
-                while (lvar.size() % 32) lvar.push_back((uint16_t)n);   // dummy variable n: uniform trip count per lane
-                lvar_ptr[l + 1] = (int)lvar.size();
-            }
-            if (lvar.size() > 65535) return bail(QLDPC_ETOOBIG, "per-layer variable lists exceed 65535 entries");
-            t.off_lvar_ptr = put(nl + 1);
-            for (int l = 0; l <= nl; ++l) b[t.off_lvar_ptr + l] = (uint16_t)lvar_ptr[l];
-            t.off_lvar_idx = put((int)lvar.size());
-            std::copy(lvar.begin(), lvar.end(), b.begin() + t.off_lvar_idx);
-            b.resize((b.size() + 7) & ~size_t(7), 0);
-            t.len = (int)b.size();
-            state = bp_layout(t).bytes;
-            // lanes per check = smallest power of two >= row weight (one lane per edge)
-            // warps per shot ("team"): as many as fit 32 warps per CTA, at most 3, and at most 15 teams (named barriers 1..15)
-            {
+            // Slot stride of the binary64 c2v array.  lane = (check of the pass, slot): a stride of 4 (mod 16) puts the slots of the
+            // consecutive checks of a pass on distinct 8-byte bank pairs, a stride that is a multiple of 16 (m = 240) puts all 8
+            // slots on the same one (measured: 53 % of the shared-memory wavefronts of the kernel were bank conflicts).  The padding
+            // costs shared memory, and resident warps are what this kernel lives on, so it is only used when it does not lower the
+            // number of resident warps the team selection below arrives at.
+            int max_layer = 0;
+            for (int l = 0; l < nl; ++l) max_layer = std::max(max_layer, p->layer_ptr[l + 1] - p->layer_ptr[l]);
+            const int lpc_bp = dc <= 4 ? 4 : (dc <= 8 ? 8 : (dc <= 16 ? 16 : 32));
+            const int passes = (max_layer + 32 / lpc_bp - 1) / (32 / lpc_bp);
+            auto build_bp = [&](int ms) -> int {          // fills b / t for slot stride ms; returns 0 or an error code
+                b.clear();
+                t.ms = ms;
+                if ((long long)dc * ms > 65535) return QLDPC_ETOOBIG;
+                t.off_var = put(dc * ms);
+                std::fill(b.begin() + t.off_var, b.begin() + t.off_var + dc * ms, kPad);
+                for (int i = 0; i < m; ++i)
+                    for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x) b[t.off_var + (x - p->row_ptr[i]) * ms + i] = (uint16_t)(4 * p->col_idx[x]);
+                t.off_col_ptr = put(n + 1);
+                for (int j = 0; j <= n; ++j) b[t.off_col_ptr + j] = (uint16_t)p->col_ptr[j];
+                t.off_col_pos = put(E);
+                t.off_col_chk = put(E);
+                for (int x = 0; x < E; ++x) {
+                    b[t.off_col_pos + x] = (uint16_t)(col_slot[x] * ms + p->row_idx[x]);
+                    b[t.off_col_chk + x] = (uint16_t)p->row_idx[x];
+                }
+                t.dvs = 0;
+                t.off_vn = 0;
+                t.n_pad = (n + 31) & ~31;
+                t.off_rowpar = put(2 * t.mw);
+                for (int i = 0; i < m; ++i)
+                    if ((p->row_ptr[i + 1] - p->row_ptr[i]) & 1) b[t.off_rowpar + 2 * (i >> 5) + ((i & 31) >> 4)] |= (uint16_t)(1u << (i & 15));
+                t.off_layer_lpc = put(nl);
+                t.off_layer_ptr = put(nl + 1);
+                for (int l = 0; l <= nl; ++l) b[t.off_layer_ptr + l] = (uint16_t)p->layer_ptr[l];
+                t.off_layer_chk = put((int)p->layer_chk.size());
+                for (size_t x = 0; x < p->layer_chk.size(); ++x) b[t.off_layer_chk + x] = (uint16_t)p->layer_chk[x];
+                std::vector<int> lvar_ptr(nl + 1, 0);
+                std::vector<uint16_t> lvar;
+                for (int l = 0; l < nl; ++l) {
+                    for (int v : layer_vars(l)) lvar.push_back((uint16_t)v);
+                    while (lvar.size() % 32) lvar.push_back((uint16_t)n);   // dummy variable n: uniform trip count per lane
+                    lvar_ptr[l + 1] = (int)lvar.size();
+                }
+                if (lvar.size() > 65535) return QLDPC_ETOOBIG;
+                t.off_lvar_ptr = put(nl + 1);
+                for (int l = 0; l <= nl; ++l) b[t.off_lvar_ptr + l] = (uint16_t)lvar_ptr[l];
+                t.off_lvar_idx = put((int)lvar.size());
+                std::copy(lvar.begin(), lvar.end(), b.begin() + t.off_lvar_idx);
+                b.resize((b.size() + 7) & ~size_t(7), 0);
+                t.len = (int)b.size();
+                return 0;
+            };
+            // warps per shot ("team") for the current b / t: as many resident warps as possible, at most 4 per team and at most 15
+            // teams (named barriers 1..15); a team only pays off when a layer has work for all of its warps.  Measured on LP118_0
+            // (11 shots fit): W = 1 / 2 / 3 / 4 -> 4.3 / 7.1 / 7.6 / 8.0e10 edge-iterations/s, i.e. the total number of resident
+            // warps is what counts, not the number of resident shots
+            auto pick_team = [&](int *W_out) -> int {     // returns the number of resident warps
+                const size_t st = bp_layout(t).bytes;
                 const size_t bb = ((size_t)t.len * 2 + 15) & ~size_t(15);
-                const int teams_fit = (int)std::min<size_t>(32, bb + state <= (size_t)kMaxSmemPerCta ? ((size_t)kMaxSmemPerCta - bb) / state : 0);
-                // a team only pays off when a layer has work for all of its warps
-                int max_layer = 0;
-                for (int l = 0; l < nl; ++l) max_layer = std::max(max_layer, p->layer_ptr[l + 1] - p->layer_ptr[l]);
-                const int lpc = dc <= 4 ? 4 : (dc <= 8 ? 8 : (dc <= 16 ? 16 : 32));
-                const int passes = (max_layer + 32 / lpc - 1) / (32 / lpc);
-                // measured on LP118_0 (11 shots fit): W = 1 / 2 / 3 / 4 -> 4.3 / 7.1 / 7.6 / 8.0e10 edge-iterations/s, i.e. the
-                // total number of resident warps is what counts, not the number of resident shots
+                const int teams_fit = (int)std::min<size_t>(32, bb + st <= (size_t)kMaxSmemPerCta ? ((size_t)kMaxSmemPerCta - bb) / st : 0);
                 int W = 1, best_warps = std::min(teams_fit, 32);
                 for (int w2 = 2; w2 <= 4 && w2 <= passes; ++w2) {
                     const int teams = std::min(teams_fit, std::min(32 / w2, 15));
                     if (teams * w2 > best_warps) { best_warps = teams * w2; W = w2; }
                 }
-                if (const char *ev = getenv("QLDPC_BP_TEAM")) { const int w2 = atoi(ev); if (w2 >= 1 && w2 <= 4 && teams_fit >= 1) W = w2; }   // tuning knob
+                *W_out = W;
+                return best_warps;
+            };
+            int W_plain = 1, W_pad = 1, ms_pad = m;
+            while (ms_pad % 16 != 4) ++ms_pad;
+            if (int e2 = build_bp(m)) return bail(e2, "code too large for the on-chip decoder tables (need m*row_weight <= 65535, n < 65535, row weight <= 32, per-layer variable lists <= 65535 entries)");
+            const int warps_plain = pick_team(&W_plain);
+            int W = W_plain;
+            if (build_bp(ms_pad) == 0 && pick_team(&W_pad) >= warps_plain) W = W_pad;
+            else { build_bp(m); W = W_plain; }
+            state = bp_layout(t).bytes;
+            // lanes per check = smallest power of two >= row weight (one lane per edge)
+            {
+                if (const char *ev = getenv("QLDPC_BP_TEAM")) { const int w2 = atoi(ev); if (w2 >= 1 && w2 <= 4) W = w2; }   // tuning knob
                 pk->bp_team = W;
 #define QLDPC_BP_PICK(L) (W == 4 ? (bp_kernel_t)bp_decode_kernel<L, 4> : (W == 3 ? (bp_kernel_t)bp_decode_kernel<L, 3> : (W == 2 ? (bp_kernel_t)bp_decode_kernel<L, 2> : (bp_kernel_t)bp_decode_kernel<L, 1>)))
                 if (dc <= 4) pk->bp = QLDPC_BP_PICK(4);
