@@ -74,6 +74,106 @@ __global__ void __launch_bounds__(256) bf_decode_kernel(GraphDev g, int max_iter
     }
 }
 
+// Sparse formulation of the same decoder (used whenever words(m) <= 32).  Both matrix-vector products of an iteration
+// have sparse inputs -- r (the unsatisfied checks) and e (the flipped variables) -- so instead of visiting every edge twice
+//   * the unsatisfied checks are compacted into a list (ballot + popc), one lane per listed check adds 1 to the counters of
+//     its variables (shared-memory atomics),
+//   * one dense pass over the n counters decides the flips and clears the counters,
+//   * "any flipped neighbour" is the OR of the bit-packed columns of H selected by the set bits of e (every lane walks its
+//     own word of e, one warp OR-reduction per residual word).
+// Same integers as the dense kernel above (kept for matrices with more than 1024 checks); ~3.5x fewer instructions.
+// Shared memory per warp: e bits [nw] | r bits [mw] | syndrome bits [mw] | counters uint32 [32*nw] | list uint16 [m rounded to 2].
+// Per CTA (after the warps): column weights uint8 [n].
+template <int VH>
+__global__ void __launch_bounds__(256) bf_sparse_kernel(GraphDev g, const uint32_t *__restrict__ hcol, int max_iter, DecodeIO io)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int per = g.nw + 2 * g.mw + 32 * g.nw + (g.m + 1) / 2;          // words per warp
+    uint32_t *eb = reinterpret_cast<uint32_t *>(smem) + (size_t)warp * per;
+    uint32_t *rb = eb + g.nw;
+    uint32_t *sb = rb + g.mw;
+    uint32_t *nuc = sb + g.mw;
+    uint16_t *list = reinterpret_cast<uint16_t *>(nuc + 32 * g.nw);
+    uint8_t *colw = reinterpret_cast<uint8_t *>(reinterpret_cast<uint32_t *>(smem) + (size_t)nwarps * per);
+    for (int j = threadIdx.x; j < g.n; j += blockDim.x) colw[j] = (uint8_t)min(255, g.col_ptr[j + 1] - g.col_ptr[j]);
+    __syncthreads();
+    const unsigned full = 0xffffffffu;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint4 *cols = reinterpret_cast<const uint4 *>(hcol);
+    for (;;) {
+        long long shot = 0;
+        if (lane == 0) shot = (long long)atomicAdd(io.work_counter, 1ull);
+        shot = __shfl_sync(full, shot, 0);
+        if (shot >= io.shots) break;
+        for (int i = lane; i < g.nw; i += 32) eb[i] = 0u;
+        for (int i = lane; i < 32 * g.nw; i += 32) nuc[i] = 0u;
+        for (int i = lane; i < g.mw; i += 32) { uint32_t w = io.syn[shot * g.mw + i]; rb[i] = w; sb[i] = w; }   // r = syndrome (:90)
+        __syncwarp();
+        int iters = max_iter;
+        bool converged = false;
+        for (int it = 0; it < max_iter; ++it) {
+            // ---- unsatisfied checks -> list
+            int cnt = 0;
+            for (int t = 0; t < g.mw; ++t) {
+                const uint32_t w = rb[t];                                    // warp-uniform
+                if ((w >> lane) & 1u) list[cnt + __popc(w & lt_mask)] = (uint16_t)(t * 32 + lane);
+                cnt += __popc(w);
+            }
+            __syncwarp();
+            // ---- nuc_j = #unsatisfied checks on j (:95)
+            for (int q = lane; q < cnt; q += 32) {
+                const int i = list[q];
+                for (int x = g.row_ptr[i]; x < g.row_ptr[i + 1]; ++x) atomicAdd(&nuc[g.col_idx[x]], 1u);
+            }
+            __syncwarp();
+            // ---- flip where nuc_j > w_j / 2 (:96); clear the counters for the next iteration
+            for (int w = 0; w < g.nw; ++w) {
+                const int j = w * 32 + lane;
+                const uint32_t c = nuc[j];
+                nuc[j] = 0u;
+                const bool flip = (j < g.n) && (2u * c > (uint32_t)colw[j < g.n ? j : 0]);
+                const uint32_t fw = __ballot_sync(full, flip);
+                if (lane == 0) eb[w] ^= fw;
+            }
+            __syncwarp();
+            // ---- r = (any flipped neighbour) xor syndrome (:97-98): OR of the columns selected by e
+            uint32_t acc[4 * VH];
+#pragma unroll
+            for (int k = 0; k < 4 * VH; ++k) acc[k] = 0u;
+            for (int w0 = 0; w0 < g.nw; w0 += 32) {
+                uint32_t word = (w0 + lane < g.nw) ? eb[w0 + lane] : 0u;
+                while (__any_sync(full, word != 0u)) {
+                    if (word) {
+                        const int j = (w0 + lane) * 32 + __ffs(word) - 1;
+                        word &= word - 1;
+                        const uint4 *c = cols + (size_t)j * (kColStride / 4);
+#pragma unroll
+                        for (int v = 0; v < VH; ++v) {
+                            const uint4 q = __ldg(c + v);
+                            acc[4 * v + 0] |= q.x; acc[4 * v + 1] |= q.y; acc[4 * v + 2] |= q.z; acc[4 * v + 3] |= q.w;
+                        }
+                    }
+                }
+            }
+            uint32_t any = 0;
+#pragma unroll
+            for (int k = 0; k < 4 * VH; ++k) {
+                if (k < g.mw) {                                              // warp-uniform
+                    const uint32_t rw = __reduce_or_sync(full, acc[k]) ^ sb[k];
+                    if (lane == 0) rb[k] = rw;
+                    any |= rw;
+                }
+            }
+            __syncwarp();
+            if (any == 0) { iters = it + 1; converged = true; break; }                     // :99-100
+        }
+        for (int w = lane; w < g.nw; w += 32) io.ehat[shot * g.nw + w] = eb[w];
+        if (lane == 0) { io.iters[shot] = iters; if (io.conv) io.conv[shot] = converged ? 1 : 0; }
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Naive greedy -- decoders.py:27-66.
 //   Repeat (at most 2n times, :47): score_v = #failing checks on v (:52-56); stop if the residual is zero (:49)

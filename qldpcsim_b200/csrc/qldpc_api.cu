@@ -125,6 +125,7 @@ struct PlanKernels {
     ms_lane_kernel_t ms_lane = nullptr;
     LaneTables lane_tab{};
     bp_kernel_t bp = nullptr;
+    const void *bf = nullptr;  // bit-flipping kernel of the plan (dense or sparse formulation)
     int bp_team = 1;           // warps per shot of the sum-product kernel
     bool regular = false;
 };
@@ -533,13 +534,25 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
         }
     } else {
         const int warps = 8;
+        const bool bf_sparse = o->dec_type == QLDPC_BF && t.mw <= 32;
         size_t per = (o->dec_type == QLDPC_BF) ? (size_t)(t.nw + 2 * t.mw) * 4 : (size_t)(t.nw + t.mw + n) * 4;
+        if (bf_sparse) per = (size_t)(t.nw + 2 * t.mw + 32 * t.nw + (m + 1) / 2) * 4;
         p->state_bytes = per;
         p->threads = warps * kWarp;
         p->shots_per_cta = warps;
-        p->smem_bytes = per * warps;
+        p->smem_bytes = per * warps + (bf_sparse ? (((size_t)n + 15) & ~size_t(15)) : 0);
         if (p->smem_bytes > (size_t)kMaxSmemPerCta) return bail(QLDPC_ETOOBIG, "code too large");
-        const void *fn = (o->dec_type == QLDPC_BF) ? (const void *)bf_decode_kernel : (const void *)ng_decode_kernel;
+        const void *fn = (const void *)ng_decode_kernel;
+        if (o->dec_type == QLDPC_BF) {
+            fn = (const void *)bf_decode_kernel;
+            if (bf_sparse) switch (col_words(t.mw) / 4) {
+                case 1: fn = (const void *)bf_sparse_kernel<1>; break;
+                case 2: fn = (const void *)bf_sparse_kernel<2>; break;
+                case 4: fn = (const void *)bf_sparse_kernel<4>; break;
+                default: fn = (const void *)bf_sparse_kernel<8>; break;
+            }
+            pk->bf = fn;
+        }
         CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta));
         int per_sm = 1;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, p->threads, p->smem_bytes));
@@ -680,7 +693,15 @@ static int launch_decode(qldpc_plan *p, const uint32_t *syn, int64_t shots, uint
         break;
     }
     case QLDPC_BF:
-        bf_decode_kernel<<<grid, p->threads, p->smem_bytes, st>>>(graph_dev(p), o.max_iter, io);
+        if (kernels_of(p)->bf == (const void *)bf_decode_kernel) {
+            bf_decode_kernel<<<grid, p->threads, p->smem_bytes, st>>>(graph_dev(p), o.max_iter, io);
+        } else {
+            GraphDev gd = graph_dev(p);
+            const uint32_t *hc = p->d_hcol;
+            int mi = o.max_iter;
+            void *args[] = {&gd, &hc, &mi, &io};
+            CU_TRY(cudaLaunchKernel(kernels_of(p)->bf, dim3(grid), dim3(p->threads), args, p->smem_bytes, st));
+        }
         break;
     case QLDPC_NG:
         ng_decode_kernel<<<grid, p->threads, p->smem_bytes, st>>>(graph_dev(p), io);
