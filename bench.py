@@ -299,7 +299,10 @@ def run_gpu(args):
                          "frac": achieved / peak, "peak_source": peak_src,
                          "bytes_per_edge_iteration": BYTES_PER_EDGE_ITER, "kernel_ms_per_step": tX + tZ,
                          "kernel_share_of_step": (tX + tZ) / (elapsed_ms / args.steps),
-                         "traffic": tr.get("dram_bytes_per_launch") if tr else None},
+                         "traffic": tr.get("dram_bytes_per_launch") if tr else None,
+                         "note": "message state stays in shared memory, so DRAM traffic is ~3 orders of magnitude below the algorithmic "
+                                 "bytes; per ncu (profiles/) the kernel is bound by instruction issue (~75 % issue-active, 2.2 warp "
+                                 "instructions per edge-iteration) and shared-memory wavefronts (~61 % of peak)"},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:

@@ -787,7 +787,8 @@ int qldpc_decode_host(qldpc_plan *p, const uint32_t *syn, int64_t shots, uint32_
     CU_TRY(cudaSetDevice(p->device));
     const Tables &t = p->tab;
     // Two pipeline slots; slot s owns streams[s], work counter s, and one quarter-open set of device buffers.
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(shots, llr ? (1 << 15) : (1 << 18)));
+    static const int64_t chunk_env = [] { const char *ev = getenv("QLDPC_HOST_CHUNK"); return ev ? atoll(ev) : 0ll; }();   // tuning knob
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(shots, chunk_env > 0 ? chunk_env : (llr ? (1 << 15) : (1 << 18))));
     const size_t b_syn = (size_t)chunk * t.mw * 4, b_e = (size_t)chunk * t.nw * 4, b_it = (size_t)chunk * 4, b_cv = (size_t)chunk,
                  b_llr = llr ? (size_t)chunk * t.n * 8 : 0;
     auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
