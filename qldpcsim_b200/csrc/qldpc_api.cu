@@ -452,7 +452,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
         if (!fn) return bail(QLDPC_ETOOBIG, "row weight not supported");
         if (blob_bytes + state > (size_t)kMaxSmemPerCta)
             return bail(QLDPC_ETOOBIG, "decoder state of one shot does not fit in 227 KB of shared memory");
-        int warps = (int)std::min<size_t>(is_ms ? kMsMaxWarps : 32, ((size_t)kMaxSmemPerCta - blob_bytes) / state);
+        int warps = (int)std::min<size_t>(is_ms ? ms_max_warps(pk->ms_tab.dc) : 32, ((size_t)kMaxSmemPerCta - blob_bytes) / state);
         const int team = is_ms ? 1 : pk->bp_team;
         if (!is_ms) warps = std::min(warps, std::min(32 / team, team > 1 ? 15 : 32));        // shots per CTA (named barriers 1..15)
         p->state_bytes = state;
