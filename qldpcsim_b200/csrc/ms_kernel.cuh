@@ -41,9 +41,9 @@
 
 namespace qldpc {
 
-// warps per CTA: 32 (64 registers per thread) for the row-weight classes 4 and 8, whose kernels fit; 24 (85 registers) for the
-// wider classes, which keep up to 32 slots per lane in registers
-__host__ __device__ constexpr int ms_max_warps(int dc_inst) { return dc_inst <= 8 ? 32 : 24; }
+// warps per CTA: 24 (768 threads, up to 85 registers per thread); the row-weight classes 4 and 8 are also instantiated for 32
+// warps (64 registers, which they fit) and use that instance when the shot state is small enough for more than 24 shots per SM
+constexpr int kMsWarps = 24, kMsWarpsBig = 32;
 constexpr int kMsMaxDv = 16;
 
 // Device view of the min-sum tables.  One uint16 blob per plan, copied to shared memory once per CTA; offsets are
@@ -277,10 +277,11 @@ __device__ __forceinline__ void ms_var_update4(uint32_t e0, uint32_t e1, int lan
     }
 }
 
-// DC: instantiated row weight (shorter rows are filled with padding edges), DV: instantiated column weight, DMIN: number of
+// MAXW: warps per CTA the instance is compiled for (launch bound), DC: instantiated row weight (shorter rows are filled with
+// padding edges), DV: instantiated column weight, DMIN: number of
 // leading regions that hold every variable (0 = guard all).
-template <int DC, int DV, int DMIN>
-__global__ void __launch_bounds__(ms_max_warps(DC) * 32, 1) ms_decode_kernel(MsTables t, const uint16_t *__restrict__ blob, MsConst c, DecodeIO io)
+template <int DC, int DV, int DMIN, int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, const uint16_t *__restrict__ blob, MsConst c, DecodeIO io)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     {   // graph tables -> shared memory (once per CTA), 16 B per thread per trip

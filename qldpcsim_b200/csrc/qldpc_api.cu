@@ -71,14 +71,14 @@ typedef void (*ms_kernel_t)(MsTables, const uint16_t *, MsConst, DecodeIO);
 // (the lifted-product / Tanner codes have column weights 3..5), DV for the others (column-regular codes such as bicycle).
 constexpr int ms_fast_dmin(int dv_inst) { return dv_inst <= 5 ? 3 : (dv_inst <= 9 ? dv_inst : 0); }
 
-template <int DC>
+template <int DC, int MAXW>
 ms_kernel_t ms_pick_dv(int dv_inst, bool fast)
 {
     switch (dv_inst) {
-    case 4: return fast ? (ms_kernel_t)ms_decode_kernel<DC, 4, ms_fast_dmin(4)> : (ms_kernel_t)ms_decode_kernel<DC, 4, 0>;
-    case 5: return fast ? (ms_kernel_t)ms_decode_kernel<DC, 5, ms_fast_dmin(5)> : (ms_kernel_t)ms_decode_kernel<DC, 5, 0>;
-    case 9: return fast ? (ms_kernel_t)ms_decode_kernel<DC, 9, ms_fast_dmin(9)> : (ms_kernel_t)ms_decode_kernel<DC, 9, 0>;
-    case 16: return (ms_kernel_t)ms_decode_kernel<DC, 16, 0>;
+    case 4: return fast ? (ms_kernel_t)ms_decode_kernel<DC, 4, ms_fast_dmin(4), MAXW> : (ms_kernel_t)ms_decode_kernel<DC, 4, 0, MAXW>;
+    case 5: return fast ? (ms_kernel_t)ms_decode_kernel<DC, 5, ms_fast_dmin(5), MAXW> : (ms_kernel_t)ms_decode_kernel<DC, 5, 0, MAXW>;
+    case 9: return fast ? (ms_kernel_t)ms_decode_kernel<DC, 9, ms_fast_dmin(9), MAXW> : (ms_kernel_t)ms_decode_kernel<DC, 9, 0, MAXW>;
+    case 16: return (ms_kernel_t)ms_decode_kernel<DC, 16, 0, MAXW>;
     }
     return nullptr;
 }
@@ -86,7 +86,7 @@ ms_kernel_t ms_pick_dv(int dv_inst, bool fast)
 // Instantiated shapes: row weight <= 4 / 8 / 16 / 24 / 32 (multiples of every lane split; shorter rows get padding edges),
 // column weight <= 4 / 5 / 9 / 16.  `full_regions` = number of leading regions that hold every variable; *dmin receives the
 // DMIN of the chosen kernel.
-ms_kernel_t ms_select(int dc, int dv, int full_regions, int *dc_inst, int *dv_inst, int *dmin)
+ms_kernel_t ms_select(int dc, int dv, int full_regions, bool big, int *dc_inst, int *dv_inst, int *dmin)
 {
     static const int dcs[] = {4, 8, 16, 24, 32}, dvs[] = {4, 5, 9, 16};
     int pc = 0, pv = 0;
@@ -98,11 +98,11 @@ ms_kernel_t ms_select(int dc, int dv, int full_regions, int *dc_inst, int *dv_in
     const bool fast = fd > 0 && full_regions >= fd;
     *dmin = fast ? fd : 0;
     switch (pc) {
-    case 4: return ms_pick_dv<4>(pv, fast);
-    case 8: return ms_pick_dv<8>(pv, fast);
-    case 16: return ms_pick_dv<16>(pv, fast);
-    case 24: return ms_pick_dv<24>(pv, fast);
-    case 32: return ms_pick_dv<32>(pv, fast);
+    case 4: return big ? ms_pick_dv<4, kMsWarpsBig>(pv, fast) : ms_pick_dv<4, kMsWarps>(pv, fast);
+    case 8: return big ? ms_pick_dv<8, kMsWarpsBig>(pv, fast) : ms_pick_dv<8, kMsWarps>(pv, fast);
+    case 16: return ms_pick_dv<16, kMsWarps>(pv, fast);
+    case 24: return ms_pick_dv<24, kMsWarps>(pv, fast);
+    case 32: return ms_pick_dv<32, kMsWarps>(pv, fast);
     }
     return nullptr;
 }
@@ -122,6 +122,7 @@ typedef void (*ms_lane_kernel_t)(LaneTables, const uint16_t *, MsConst, DecodeIO
 struct PlanKernels {
     ms_kernel_t ms = nullptr;
     MsTables ms_tab{};
+    int ms_full_regions = 0;
     ms_lane_kernel_t ms_lane = nullptr;
     LaneTables lane_tab{};
     bp_kernel_t bp = nullptr;
@@ -286,8 +287,9 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
                 int dmin_true = n ? *std::min_element(cw.begin(), cw.end()) : 0;
                 full_regions = std::min(dmin_true, dv);
             }
+            pk->ms_full_regions = full_regions;
             int dc_inst = 0, dv_inst = 0, dmin = 0;
-            pk->ms = ms_select(dc, dv, full_regions, &dc_inst, &dv_inst, &dmin);
+            pk->ms = ms_select(dc, dv, full_regions, false, &dc_inst, &dv_inst, &dmin);
             if (!pk->ms) return bail(QLDPC_ETOOBIG, "min-sum kernels are instantiated for row weight <= 32 and column weight <= 16");
             MsGraphView gv{m, n, E, p->row_ptr.data(), p->col_idx.data(), p->col_ptr.data(), p->row_idx.data(), nl, p->layer_ptr.data(), p->layer_chk.data()};
             MsPlanLayout pl;
@@ -452,7 +454,14 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
         if (!fn) return bail(QLDPC_ETOOBIG, "row weight not supported");
         if (blob_bytes + state > (size_t)kMaxSmemPerCta)
             return bail(QLDPC_ETOOBIG, "decoder state of one shot does not fit in 227 KB of shared memory");
-        int warps = (int)std::min<size_t>(is_ms ? ms_max_warps(pk->ms_tab.dc) : 32, ((size_t)kMaxSmemPerCta - blob_bytes) / state);
+        const int warps_fit = (int)std::min<size_t>(64, ((size_t)kMaxSmemPerCta - blob_bytes) / state);
+        int warps = std::min(warps_fit, is_ms ? kMsWarps : 32);
+        if (is_ms && warps_fit > kMsWarps && pk->ms_tab.dc <= 8) {           // small shot state: the 32-warp instance
+            int a1, a2, a3;
+            pk->ms = ms_select(dc, dv, pk->ms_full_regions, true, &a1, &a2, &a3);
+            fn = (const void *)pk->ms;
+            warps = std::min(warps_fit, kMsWarpsBig);
+        }
         const int team = is_ms ? 1 : pk->bp_team;
         if (!is_ms) warps = std::min(warps, std::min(32 / team, team > 1 ? 15 : 32));        // shots per CTA (named barriers 1..15)
         p->state_bytes = state;
