@@ -59,8 +59,11 @@ def main():
                " (ncu --set full, bench.py --steps 2 --warmup 3 --no-cpu, 10^6 shots per launch)",
                "dram_bytes_per_launch": sum(per) / len(per), "per_launch": per},
               open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
-    print(open(os.path.join(out, "launch_shares.txt")).read())
-    print(summ)
+    try:
+        print(open(os.path.join(out, "launch_shares.txt")).read())
+        print(summ)
+    except BrokenPipeError:
+        pass
 
 
 if __name__ == "__main__":
