@@ -295,7 +295,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": shots * 4 * (mzw + mxw),
                     "d2h_bytes_per_step": shots * 2 * (4 * nw + 4 + 1), "api": "qldpc_decode_host (pinned host buffers), X then Z"},
             "gpu_launches": int(launches) * world,
-            "roofline": {"bound": "hbm", "kernel": "ms_decode_kernel<8,5,3,24>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "ms_decode_kernel<8,5,3,24,1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src,
                          "bytes_per_edge_iteration": BYTES_PER_EDGE_ITER, "kernel_ms_per_step": tX + tZ,
                          "kernel_share_of_step": (tX + tZ) / (elapsed_ms / args.steps),

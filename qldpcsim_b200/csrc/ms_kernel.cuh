@@ -81,6 +81,7 @@ struct MsSmemLayout {
                    // scratch c2v word of the padding edges
     int off_par;   // uint32 [mw]
     int off_syn;   // uint32 [mw]
+    int off_team;  // 16 bytes: shot mailbox (int64) + unsatisfied-check count (int32) of a multi-warp team
     int zero_words;
     int bytes;     // multiple of 128: S_j' and every c2v word of j' sit on bank j' mod 32
 };
@@ -94,6 +95,8 @@ __host__ __device__ inline MsSmemLayout ms_layout(const MsTables &t)
     l.zero_words = o / 4;
     l.off_par = o; o += 4 * t.mw;
     l.off_syn = o; o += 4 * t.mw;
+    o = (o + 7) & ~7;
+    l.off_team = o; o += 16;
     l.bytes = (o + 127) & ~127;
     return l;
 }
@@ -129,7 +132,8 @@ struct MsAddr {          // shared-window byte addresses, warp-uniform
 // compare+select chains.  The sign of b_k is the sign of v2c_k (v2c is never -0.0: it is a difference whose minuend is never
 // -0.0, and rounding keeps signs).  beta < 0: the caller passes |beta| and folds the extra sign into `sgn_extra`.
 template <int DC, int LPC>
-__device__ __forceinline__ void ms_check_phase(int qb, int qe, int lane, const MsAddr &A, double prior, double beta, uint32_t sgn_extra)
+__device__ __forceinline__ void ms_check_phase(int qb, int qe, int q_first, int q_stride, int lane, const MsAddr &A, double prior, double beta,
+                                               uint32_t sgn_extra)
 {
     static_assert(DC % LPC == 0, "row-weight classes are multiples of the lane split");
     constexpr int SPL = DC / LPC;                   // slots per lane
@@ -137,7 +141,7 @@ __device__ __forceinline__ void ms_check_phase(int qb, int qe, int lane, const M
     const int h = lane % LPC;                       // which slice of the row
     const int k0 = h * SPL;                         // first slot of the lane
     const float inf = __int_as_float(0x7f800000);
-    for (int q0 = qb; q0 < qe; q0 += CPP) {
+    for (int q0 = q_first; q0 < qe; q0 += q_stride) {         // q_first = qb + sub * CPP, q_stride = W * CPP for a team of W warps
         const int q = q0 + lane / LPC;
         const bool act = q < qe;
         const uint32_t i = sld_u16(A.layer_chk + 2u * (uint32_t)(act ? q : qb));
@@ -277,10 +281,10 @@ __device__ __forceinline__ void ms_var_update4(uint32_t e0, uint32_t e1, int lan
     }
 }
 
-// MAXW: warps per CTA the instance is compiled for (launch bound), DC: instantiated row weight (shorter rows are filled with
+// W: warps per shot ("team", see below), MAXW: warps per CTA the instance is compiled for (launch bound), DC: instantiated row weight (shorter rows are filled with
 // padding edges), DV: instantiated column weight, DMIN: number of
 // leading regions that hold every variable (0 = guard all).
-template <int DC, int DV, int DMIN, int MAXW>
+template <int DC, int DV, int DMIN, int MAXW, int W>
 __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, const uint16_t *__restrict__ blob, MsConst c, DecodeIO io)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -297,7 +301,19 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
     uint32_t tab;                                                         // shared-window address of the CTA tables
     // opaque to the optimiser on purpose: a plain __cvta_generic_to_shared gets rematerialised (S2UR + ULEA) in every loop
     asm volatile("{ .reg .u64 t64; cvta.to.shared.u64 t64, %1; cvt.u32.u64 %0, t64; }" : "=r"(tab) : "l"(smem));
-    const uint32_t wbase = tab + (uint32_t)ms_table_bytes(t) + (uint32_t)warp * (uint32_t)lay.bytes;
+    // W > 1: a team of W warps shares one shot.  Codes whose shot state is large (LP118_2, Tanner: 19 KB) fit only ~10 shots per
+    // SM, and 10 warps cannot hide the latency of their dependent shared-memory / FP64 chains; the team splits the passes of the
+    // check phase and the trips of the variable phase and meets at a named barrier between the phases.  Every edge and every
+    // variable is still computed by exactly one lane in the same arithmetic order, so the result does not depend on W.
+    const int team = warp / W, sub = warp % W;
+    constexpr int TT = 32 * W;
+    const int tl = sub * 32 + lane;                                       // thread index within the team
+    const uint32_t wbase = tab + (uint32_t)ms_table_bytes(t) + (uint32_t)team * (uint32_t)lay.bytes;
+    auto team_sync = [&]() {
+        if constexpr (W == 1) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" :: "r"(team + 1), "r"(TT) : "memory");
+    };
+    const uint32_t team_box = wbase + lay.off_team;                       // [0..7] shot mailbox, [8..11] unsatisfied-check count
     MsAddr A;
     A.chk = tab + 2u * t.off_chk;
     A.layer_chk = tab + 2u * t.off_layer_chk;
@@ -318,29 +334,47 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
     const long long n_pos = io.shot_list ? (long long)*io.list_len : io.shots;
     for (;;) {
         long long shot = 0;
-        if (lane == 0) {
+        if (tl == 0) {
             shot = (long long)atomicAdd(io.work_counter, 1ull);
             if (io.shot_list && shot < n_pos) shot = io.shot_list[shot];
             else if (io.shot_list) shot = -1;
+            if constexpr (W > 1) asm volatile("st.shared.u64 [%0], %1;" :: "r"(team_box), "l"(shot) : "memory");
         }
-        shot = __shfl_sync(full, shot, 0);
+        if constexpr (W == 1) shot = __shfl_sync(full, shot, 0);
+        else {
+            team_sync();
+            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(shot) : "r"(team_box) : "memory");
+        }
         if (shot < 0 || shot >= io.shots) break;
 
         // ---- initial state: c2v = 0 (decoders.py:150), S = 0, residual = syndrome (+ H.1 if the all-zero sums decide 1)
-        for (int i = lane * 4; i < lay.zero_words; i += 128)
+        for (int i = tl * 4; i < lay.zero_words; i += 4 * TT)
             asm volatile("st.shared.v4.f32 [%0], {%1,%1,%1,%1};" :: "r"(A.c2v + 4u * i), "f"(0.0f) : "memory");
-        __syncwarp();
-        if (lane == 0) sst_u32(A.S + n4 + 4u, 0x7f800000u);            // S[n+1] = +inf: the padding edges
+        team_sync();
+        if (tl == 0) sst_u32(A.S + n4 + 4u, 0x7f800000u);              // S[n+1] = +inf: the padding edges
         int unsat = 0;
-        for (int i = lane; i < t.mw; i += 32) {
-            const uint32_t w = io.syn[shot * t.mw + i];
-            const uint32_t p0 = init_bit ? (w ^ sld_u32(rowpar + 4u * i)) : w;
-            sst_u32(A.syn + 4u * i, w);
-            sst_u32(A.par + 4u * i, p0);
-            unsat += __popc(p0);
+        if (sub == 0) {
+            for (int i = lane; i < t.mw; i += 32) {
+                const uint32_t w = io.syn[shot * t.mw + i];
+                const uint32_t p0 = init_bit ? (w ^ sld_u32(rowpar + 4u * i)) : w;
+                sst_u32(A.syn + 4u * i, w);
+                sst_u32(A.par + 4u * i, p0);
+                unsat += __popc(p0);
+            }
+            unsat = __reduce_add_sync(full, unsat);
+            if constexpr (W > 1) { if (lane == 0) sst_u32(team_box + 8u, (uint32_t)unsat); }
         }
-        unsat = __reduce_add_sync(full, unsat);
-        __syncwarp();
+        team_sync();
+        // unsat: a register in every lane for W == 1; for a team the shared word is the truth and `unsat` its copy after a barrier
+        auto settle = [&](int delta) {
+            delta = __reduce_add_sync(full, delta);
+            if constexpr (W == 1) { unsat += delta; __syncwarp(); }
+            else {
+                if (lane == 0 && delta != 0) asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(team_box + 8u), "r"(delta) : "memory");
+                team_sync();
+                unsat = (int)sld_u32(team_box + 8u);      // read by every warp before it can reach the next barrier; next written after it
+            }
+        };
 
         bool converged = false;
         int it = 0;
@@ -349,13 +383,12 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
             // phase visits EVERY variable (the reference recomputes all posteriors; a variable outside layer 0 has
             // posterior L, which may be negative for p > 1/2)
             const int qb = sld_u16(layer_rec), qe = sld_u16(layer_rec + 2u);
-            ms_check_phase<DC, 1>(qb, qe, lane, A, c.Lf, c.abeta, c.sgn);
-            __syncwarp();
+            ms_check_phase<DC, 1>(qb, qe, qb + 32 * sub, 32 * W, lane, A, c.Lf, c.abeta, c.sgn);
+            team_sync();
             int delta = 0;
-            for (int q = lane; q < t.n_pad; q += 64)
+            for (int q = 64 * sub + lane; q < t.n_pad; q += 64 * W)
                 ms_var_update2<DV, DMIN>(q < n ? 4u * q : n4, q + 32 < n ? 4u * (q + 32) : n4, lane, A, t, Tf, delta);
-            unsat += __reduce_add_sync(full, delta);
-            __syncwarp();
+            settle(delta);
             converged = unsat == 0;
         }
         for (; it < c.max_iter && !converged; ++it) {
@@ -364,25 +397,26 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
                 uint32_t r0, r1, r2, r3;                                       // the layer's 16-byte record
                 asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(layer_rec + 16u * l));
                 const int qb = r0 & 0xffffu, qe = r0 >> 16, lpc = r1 & 0xffffu;
-                if (lpc == 1) ms_check_phase<DC, 1>(qb, qe, lane, A, c.L, c.abeta, c.sgn);
-                else if (lpc == 2) ms_check_phase<DC, 2>(qb, qe, lane, A, c.L, c.abeta, c.sgn);
-                else if (lpc == 4) ms_check_phase<DC, 4>(qb, qe, lane, A, c.L, c.abeta, c.sgn);
-                else if constexpr (DC % 8 == 0) ms_check_phase<DC, 8>(qb, qe, lane, A, c.L, c.abeta, c.sgn);   // DC = 4: lpc <= 4
-                __syncwarp();
+                if (lpc == 1) ms_check_phase<DC, 1>(qb, qe, qb + 32 * sub, 32 * W, lane, A, c.L, c.abeta, c.sgn);
+                else if (lpc == 2) ms_check_phase<DC, 2>(qb, qe, qb + 16 * sub, 16 * W, lane, A, c.L, c.abeta, c.sgn);
+                else if (lpc == 4) ms_check_phase<DC, 4>(qb, qe, qb + 8 * sub, 8 * W, lane, A, c.L, c.abeta, c.sgn);
+                else if constexpr (DC % 8 == 0) ms_check_phase<DC, 8>(qb, qe, qb + 4 * sub, 4 * W, lane, A, c.L, c.abeta, c.sgn);   // DC = 4: lpc <= 4
+                team_sync();
                 // ---------------- variable-node phase (decoders.py:172-174) on the variables whose sums changed.  Every
                 // lane runs the same number of trips (lists are padded to whole trips with the dummy variable n).
                 const int vb = r1 >> 16, ve = r2 & 0xffffu;
                 int delta = 0;
-                int q = vb + lane;
-                for (; q + 32 < ve; q += 64)
+                const int P = (ve - vb) >> 5;                                  // pair-trips of the layer; quad trips go round-robin to the warps
+                for (int p = 2 * sub; p + 1 < P; p += 2 * W) {
+                    const int q = vb + 32 * p + lane;
                     ms_var_update4<DV, DMIN>(sld_u32(lvar + 4u * q), sld_u32(lvar + 4u * q + 128u), lane, A, t, Tf, delta);
-                if (q < ve) {
-                    const uint32_t e = sld_u32(lvar + 4u * q);
-                    if (r2 >> 16) ms_var_update1<DV, DMIN>(e & 0xffffu, lane, A, t, Tf, delta);      // last pair-trip holds one sub-group only
+                }
+                if ((P & 1) && ((P >> 1) % W) == sub) {                        // odd pair-trip at the end
+                    const uint32_t e = sld_u32(lvar + 4u * (uint32_t)(ve - 32 + lane));
+                    if (r2 >> 16) ms_var_update1<DV, DMIN>(e & 0xffffu, lane, A, t, Tf, delta);      // it holds one sub-group only
                     else ms_var_update2<DV, DMIN>(e & 0xffffu, e >> 16, lane, A, t, Tf, delta);
                 }
-                unsat += __reduce_add_sync(full, delta);
-                __syncwarp();
+                settle(delta);
                 // ---------------- H e == syndrome ?  (decoders.py:175-176)
                 if (unsat == 0) { converged = true; break; }
             }
@@ -391,30 +425,34 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
         // very first step leaves it == 0), else max_iter (:182)
         const int iters = (converged && it == 0) ? 1 : it;
         // ---- outputs: e_j = (S_j' < Tf)
-        for (int w = 0; w < t.nw; ++w) {
+        for (int w = sub; w < t.nw; w += W) {
             const int j = w * 32 + lane;
             const uint32_t bits = __ballot_sync(full, j < n && c.max_iter > 0 && sld_f32(A.S + sld_u16(unperm + 2u * j)) < Tf);
             if (lane == 0) io.ehat[shot * t.nw + w] = bits;
         }
-        if (lane == 0) {
+        if (tl == 0) {
             io.iters[shot] = iters;
             if (io.conv) io.conv[shot] = converged ? 1 : 0;
         }
         if (io.llr) {
             double *dst = io.llr + shot * (long long)n;
-            for (int j = lane; j < n; j += 32) dst[j] = __dadd_rn(c.L, (double)sld_f32(A.S + sld_u16(unperm + 2u * j)));
+            for (int j = tl; j < n; j += TT) dst[j] = __dadd_rn(c.L, (double)sld_f32(A.S + sld_u16(unperm + 2u * j)));
         }
         if (!converged && io.fail_count) {
             int slot = 0;
-            if (lane == 0) slot = atomicAdd(io.fail_count, 1);
-            slot = __shfl_sync(full, slot, 0);
+            if (tl == 0) {
+                slot = atomicAdd(io.fail_count, 1);
+                if (slot < io.fail_cap) io.fail_shot[slot] = (int)shot;
+                if constexpr (W > 1) sst_u32(team_box, (uint32_t)slot);       // the mailbox is free: every warp has read the shot index
+            }
+            if constexpr (W == 1) slot = __shfl_sync(full, slot, 0);
+            else { team_sync(); slot = (int)sld_u32(team_box); }
             if (slot < io.fail_cap) {
-                if (lane == 0) io.fail_shot[slot] = (int)shot;
                 double *dst = io.fail_llr + (long long)slot * n;
-                for (int j = lane; j < n; j += 32) dst[j] = __dadd_rn(c.L, (double)sld_f32(A.S + sld_u16(unperm + 2u * j)));
+                for (int j = tl; j < n; j += TT) dst[j] = __dadd_rn(c.L, (double)sld_f32(A.S + sld_u16(unperm + 2u * j)));
             }
         }
-        __syncwarp();
+        team_sync();
     }
 }
 

@@ -42,11 +42,13 @@ struct MsPlanLayout {
 
 namespace msplan {
 
-inline int lanes_per_check(int layer_checks, int dc_inst)
+// lanes per check of a layer: the largest power of two (<= 8, dividing the row-weight class) that keeps the layer within one
+// pass of the `team_warps` warps that share a shot
+inline int lanes_per_check(int layer_checks, int dc_inst, int team_warps)
 {
     const int lc = std::max(1, layer_checks);
     int lpc = 1;
-    while (lpc < 8 && lpc * 2 * lc <= 32 && lpc * 2 <= std::max(1, dc_inst)) lpc *= 2;
+    while (lpc < 8 && lpc * 2 * lc <= 32 * team_warps && lpc * 2 <= std::max(1, dc_inst)) lpc *= 2;
     return lpc;
 }
 
@@ -222,7 +224,7 @@ struct Evaluator {
 
 // dc_inst / dv_inst / dmin are the shape of the kernel instance (see qldpc_api.cu: ms_select); `search` enables the unit
 // order search (bounded number of evaluations).
-inline void ms_plan_layout(const MsGraphView &g, int dc_inst, int dv_inst, int dmin, bool search, MsPlanLayout &L)
+inline void ms_plan_layout(const MsGraphView &g, int dc_inst, int dv_inst, int dmin, bool search, MsPlanLayout &L, int team_warps = 1)
 {
     const int n = g.n;
     L.dc_inst = dc_inst; L.dv_inst = dv_inst; L.dmin = dmin;
@@ -253,7 +255,7 @@ inline void ms_plan_layout(const MsGraphView &g, int dc_inst, int dv_inst, int d
             for (int x = g.row_ptr[i]; x < g.row_ptr[i + 1]; ++x) L.edge_rank[x] = fill[g.col_idx[x]]++;
     }
     L.lpc.resize(g.nl);
-    for (int l = 0; l < g.nl; ++l) L.lpc[l] = msplan::lanes_per_check(g.layer_ptr[l + 1] - g.layer_ptr[l], dc_inst);
+    for (int l = 0; l < g.nl; ++l) L.lpc[l] = msplan::lanes_per_check(g.layer_ptr[l + 1] - g.layer_ptr[l], dc_inst, team_warps);
 
     msplan::Evaluator ev(g, L);
     long long best = ev.total(false);

@@ -71,14 +71,14 @@ typedef void (*ms_kernel_t)(MsTables, const uint16_t *, MsConst, DecodeIO);
 // (the lifted-product / Tanner codes have column weights 3..5), DV for the others (column-regular codes such as bicycle).
 constexpr int ms_fast_dmin(int dv_inst) { return dv_inst <= 5 ? 3 : (dv_inst <= 9 ? dv_inst : 0); }
 
-template <int DC, int MAXW>
+template <int DC, int MAXW, int W>
 ms_kernel_t ms_pick_dv(int dv_inst, bool fast)
 {
     switch (dv_inst) {
-    case 4: return fast ? (ms_kernel_t)ms_decode_kernel<DC, 4, ms_fast_dmin(4), MAXW> : (ms_kernel_t)ms_decode_kernel<DC, 4, 0, MAXW>;
-    case 5: return fast ? (ms_kernel_t)ms_decode_kernel<DC, 5, ms_fast_dmin(5), MAXW> : (ms_kernel_t)ms_decode_kernel<DC, 5, 0, MAXW>;
-    case 9: return fast ? (ms_kernel_t)ms_decode_kernel<DC, 9, ms_fast_dmin(9), MAXW> : (ms_kernel_t)ms_decode_kernel<DC, 9, 0, MAXW>;
-    case 16: return (ms_kernel_t)ms_decode_kernel<DC, 16, 0, MAXW>;
+    case 4: return fast ? (ms_kernel_t)ms_decode_kernel<DC, 4, ms_fast_dmin(4), MAXW, W> : (ms_kernel_t)ms_decode_kernel<DC, 4, 0, MAXW, W>;
+    case 5: return fast ? (ms_kernel_t)ms_decode_kernel<DC, 5, ms_fast_dmin(5), MAXW, W> : (ms_kernel_t)ms_decode_kernel<DC, 5, 0, MAXW, W>;
+    case 9: return fast ? (ms_kernel_t)ms_decode_kernel<DC, 9, ms_fast_dmin(9), MAXW, W> : (ms_kernel_t)ms_decode_kernel<DC, 9, 0, MAXW, W>;
+    case 16: return (ms_kernel_t)ms_decode_kernel<DC, 16, 0, MAXW, W>;
     }
     return nullptr;
 }
@@ -86,7 +86,8 @@ ms_kernel_t ms_pick_dv(int dv_inst, bool fast)
 // Instantiated shapes: row weight <= 4 / 8 / 16 / 24 / 32 (multiples of every lane split; shorter rows get padding edges),
 // column weight <= 4 / 5 / 9 / 16.  `full_regions` = number of leading regions that hold every variable; *dmin receives the
 // DMIN of the chosen kernel.
-ms_kernel_t ms_select(int dc, int dv, int full_regions, bool big, int *dc_inst, int *dv_inst, int *dmin)
+// variant: 0 = 24 warps per CTA, 1 = 32 warps per CTA (row-weight classes 4 and 8), 2 = teams of two warps per shot (class 8)
+ms_kernel_t ms_select(int dc, int dv, int full_regions, int variant, int *dc_inst, int *dv_inst, int *dmin)
 {
     static const int dcs[] = {4, 8, 16, 24, 32}, dvs[] = {4, 5, 9, 16};
     int pc = 0, pv = 0;
@@ -98,11 +99,11 @@ ms_kernel_t ms_select(int dc, int dv, int full_regions, bool big, int *dc_inst, 
     const bool fast = fd > 0 && full_regions >= fd;
     *dmin = fast ? fd : 0;
     switch (pc) {
-    case 4: return big ? ms_pick_dv<4, kMsWarpsBig>(pv, fast) : ms_pick_dv<4, kMsWarps>(pv, fast);
-    case 8: return big ? ms_pick_dv<8, kMsWarpsBig>(pv, fast) : ms_pick_dv<8, kMsWarps>(pv, fast);
-    case 16: return ms_pick_dv<16, kMsWarps>(pv, fast);
-    case 24: return ms_pick_dv<24, kMsWarps>(pv, fast);
-    case 32: return ms_pick_dv<32, kMsWarps>(pv, fast);
+    case 4: return variant == 1 ? ms_pick_dv<4, kMsWarpsBig, 1>(pv, fast) : ms_pick_dv<4, kMsWarps, 1>(pv, fast);
+    case 8: return variant == 1 ? ms_pick_dv<8, kMsWarpsBig, 1>(pv, fast) : (variant == 2 ? ms_pick_dv<8, kMsWarps, 2>(pv, fast) : ms_pick_dv<8, kMsWarps, 1>(pv, fast));
+    case 16: return ms_pick_dv<16, kMsWarps, 1>(pv, fast);
+    case 24: return ms_pick_dv<24, kMsWarps, 1>(pv, fast);
+    case 32: return ms_pick_dv<32, kMsWarps, 1>(pv, fast);
     }
     return nullptr;
 }
@@ -123,6 +124,7 @@ struct PlanKernels {
     ms_kernel_t ms = nullptr;
     MsTables ms_tab{};
     int ms_full_regions = 0;
+    int ms_team = 1;           // warps per shot of the warp-per-shot min-sum kernel
     ms_lane_kernel_t ms_lane = nullptr;
     LaneTables lane_tab{};
     bp_kernel_t bp = nullptr;
@@ -289,11 +291,29 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             }
             pk->ms_full_regions = full_regions;
             int dc_inst = 0, dv_inst = 0, dmin = 0;
-            pk->ms = ms_select(dc, dv, full_regions, false, &dc_inst, &dv_inst, &dmin);
+            pk->ms = ms_select(dc, dv, full_regions, 0, &dc_inst, &dv_inst, &dmin);
             if (!pk->ms) return bail(QLDPC_ETOOBIG, "min-sum kernels are instantiated for row weight <= 32 and column weight <= 16");
             MsGraphView gv{m, n, E, p->row_ptr.data(), p->col_idx.data(), p->col_ptr.data(), p->row_idx.data(), nl, p->layer_ptr.data(), p->layer_chk.data()};
             MsPlanLayout pl;
             ms_plan_layout(gv, dc_inst, dv_inst, dmin, /*search=*/true, pl);
+            // Teams of two warps per shot: when the shot state allows only few shots per SM (LP118_2, Tanner: 10), one warp per
+            // shot leaves the schedulers idle.  Decided on the state size (tables are ~10-35 KB), row-weight class 8 only.
+            {
+                MsTables probe{};
+                probe.n = n; probe.mw = t.mw; probe.c2v_words = pl.c2v_words;
+                const size_t st = ms_layout(probe).bytes;
+                int max_layer2 = 0;
+                for (int l = 0; l < nl; ++l) max_layer2 = std::max(max_layer2, p->layer_ptr[l + 1] - p->layer_ptr[l]);
+                int W = (dc_inst == 8 && st * 13 > (size_t)kMaxSmemPerCta - 24 * 1024 && max_layer2 >= 16) ? 2 : 1;
+                if (const char *ev = getenv("QLDPC_MS_TEAM")) { const int w2 = atoi(ev); if (w2 == 1 || (w2 == 2 && dc_inst == 8)) W = w2; }   // tuning knob
+                pk->ms_team = W;
+                if (W == 2) {
+                    pl = MsPlanLayout();
+                    ms_plan_layout(gv, dc_inst, dv_inst, dmin, /*search=*/true, pl, 2);
+                    int a1, a2, a3;
+                    pk->ms = ms_select(dc, dv, full_regions, 2, &a1, &a2, &a3);
+                }
+            }
             p->plan_wavefronts = pl.wavefronts; p->plan_wavefronts_ideal = pl.ideal;
             mt.m = m; mt.n = n; mt.E = E; mt.dc = dc_inst; mt.dv = dv; mt.nl = nl; mt.mw = t.mw; mt.nw = t.nw;
             mt.n_pad = (n + 63) & ~63;
@@ -456,13 +476,14 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             return bail(QLDPC_ETOOBIG, "decoder state of one shot does not fit in 227 KB of shared memory");
         const int warps_fit = (int)std::min<size_t>(64, ((size_t)kMaxSmemPerCta - blob_bytes) / state);
         int warps = std::min(warps_fit, is_ms ? kMsWarps : 32);
-        if (is_ms && warps_fit > kMsWarps && pk->ms_tab.dc <= 8) {           // small shot state: the 32-warp instance
+        if (is_ms && pk->ms_team == 1 && warps_fit > kMsWarps && pk->ms_tab.dc <= 8) {           // small shot state: the 32-warp instance
             int a1, a2, a3;
-            pk->ms = ms_select(dc, dv, pk->ms_full_regions, true, &a1, &a2, &a3);
+            pk->ms = ms_select(dc, dv, pk->ms_full_regions, 1, &a1, &a2, &a3);
             fn = (const void *)pk->ms;
             warps = std::min(warps_fit, kMsWarpsBig);
         }
-        const int team = is_ms ? 1 : pk->bp_team;
+        const int team = is_ms ? pk->ms_team : pk->bp_team;
+        if (is_ms && team > 1) warps = std::min(warps, std::min(kMsWarps / team, 15));          // shots per CTA (named barriers 1..15)
         if (!is_ms) warps = std::min(warps, std::min(32 / team, team > 1 ? 15 : 32));        // shots per CTA (named barriers 1..15)
         p->state_bytes = state;
         p->threads = warps * team * kWarp;
