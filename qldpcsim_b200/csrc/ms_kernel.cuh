@@ -2,8 +2,9 @@
 //
 // Semantics: decoders.py:110-182 of the reference (bit-level spec in SURVEY.md App. A.1, restated on the CPU
 // in oracle/qldpc_oracle.c:ms_decode_one).  Mapping:
-//   * one WARP owns one shot from its first layer step to its exit and then pulls the next shot from a
-//     global dispenser (shots converge after 1..max_iter iterations, so there are no lock-step batches);
+//   * one WARP -- or, for codes whose shot state leaves room for only ~10 shots per SM, a TEAM of two warps -- owns one
+//     shot from its first layer step to its exit and then pulls the next shot from a global dispenser (shots converge
+//     after 1..max_iter iterations, so there are no lock-step batches);
 //   * the whole message state of the shot lives in shared memory: c2v as binary32 per edge, the binary32
 //     column sums S_j, the residual syndrome H e + s as bit words;
 //   * VARIABLE-MAJOR message layout.  Variables are renumbered by descending column weight (stable, so the
@@ -19,7 +20,8 @@
 //     exactly what decoders.py:173,:177 computes (prior = binary32-rounded L during the very first layer
 //     step, decoders.py:148-149, L afterwards);
 //   * check phase: LPC = 1, 2, 4 or 8 lanes share one check (chosen per layer so that the layer fills the
-//     warp); min / second min are taken on the ROUNDED per-edge values in binary32 (see ms_check_phase);
+//     warp); min / second min are taken on the ROUNDED per-edge values in binary32 (see ms_check_phase); rows shorter
+//     than the instantiated row weight are filled with padding edges whose posterior is +inf (no predicates);
 //   * variable phase: lane <-> two variables adjacent to the layer per trip, re-summing ALL their c2v in
 //     ascending check order in binary32 (decoders.py:172).  Layers need not be column-disjoint
 //     (simulator.py:230-234 hands the decoder the partition of the OTHER matrix), so the two phases are
@@ -132,7 +134,7 @@ struct MsAddr {          // shared-window byte addresses, warp-uniform
 // compare+select chains.  The sign of b_k is the sign of v2c_k (v2c is never -0.0: it is a difference whose minuend is never
 // -0.0, and rounding keeps signs).  beta < 0: the caller passes |beta| and folds the extra sign into `sgn_extra`.
 template <int DC, int LPC>
-__device__ __forceinline__ void ms_check_phase(int qb, int qe, int q_first, int q_stride, int lane, const MsAddr &A, double prior, double beta,
+__device__ __forceinline__ void ms_check_phase(int qb, int qe, int sub, int team_warps, int lane, const MsAddr &A, double prior, double beta,
                                                uint32_t sgn_extra)
 {
     static_assert(DC % LPC == 0, "row-weight classes are multiples of the lane split");
@@ -141,7 +143,7 @@ __device__ __forceinline__ void ms_check_phase(int qb, int qe, int q_first, int 
     const int h = lane % LPC;                       // which slice of the row
     const int k0 = h * SPL;                         // first slot of the lane
     const float inf = __int_as_float(0x7f800000);
-    for (int q0 = q_first; q0 < qe; q0 += q_stride) {         // q_first = qb + sub * CPP, q_stride = W * CPP for a team of W warps
+    for (int q0 = qb + sub * CPP; q0 < qe; q0 += team_warps * CPP) {   // the passes of a layer go round-robin to the warps of the team
         const int q = q0 + lane / LPC;
         const bool act = q < qe;
         const uint32_t i = sld_u16(A.layer_chk + 2u * (uint32_t)(act ? q : qb));
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
             // phase visits EVERY variable (the reference recomputes all posteriors; a variable outside layer 0 has
             // posterior L, which may be negative for p > 1/2)
             const int qb = sld_u16(layer_rec), qe = sld_u16(layer_rec + 2u);
-            ms_check_phase<DC, 1>(qb, qe, qb + 32 * sub, 32 * W, lane, A, c.Lf, c.abeta, c.sgn);
+            ms_check_phase<DC, 1>(qb, qe, sub, W, lane, A, c.Lf, c.abeta, c.sgn);
             team_sync();
             int delta = 0;
             for (int q = 64 * sub + lane; q < t.n_pad; q += 64 * W)
@@ -397,10 +399,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
                 uint32_t r0, r1, r2, r3;                                       // the layer's 16-byte record
                 asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(layer_rec + 16u * l));
                 const int qb = r0 & 0xffffu, qe = r0 >> 16, lpc = r1 & 0xffffu;
-                if (lpc == 1) ms_check_phase<DC, 1>(qb, qe, qb + 32 * sub, 32 * W, lane, A, c.L, c.abeta, c.sgn);
-                else if (lpc == 2) ms_check_phase<DC, 2>(qb, qe, qb + 16 * sub, 16 * W, lane, A, c.L, c.abeta, c.sgn);
-                else if (lpc == 4) ms_check_phase<DC, 4>(qb, qe, qb + 8 * sub, 8 * W, lane, A, c.L, c.abeta, c.sgn);
-                else if constexpr (DC % 8 == 0) ms_check_phase<DC, 8>(qb, qe, qb + 4 * sub, 4 * W, lane, A, c.L, c.abeta, c.sgn);   // DC = 4: lpc <= 4
+                if (lpc == 1) ms_check_phase<DC, 1>(qb, qe, sub, W, lane, A, c.L, c.abeta, c.sgn);
+                else if (lpc == 2) ms_check_phase<DC, 2>(qb, qe, sub, W, lane, A, c.L, c.abeta, c.sgn);
+                else if (lpc == 4) ms_check_phase<DC, 4>(qb, qe, sub, W, lane, A, c.L, c.abeta, c.sgn);
+                else if constexpr (DC % 8 == 0) ms_check_phase<DC, 8>(qb, qe, sub, W, lane, A, c.L, c.abeta, c.sgn);   // DC = 4: lpc <= 4
                 team_sync();
                 // ---------------- variable-node phase (decoders.py:172-174) on the variables whose sums changed.  Every
                 // lane runs the same number of trips (lists are padded to whole trips with the dummy variable n).
