@@ -152,6 +152,31 @@ class Pipeline:
         return counters
 
 
+    def decode_host(self, syn_z, syn_x, out_x, out_z):
+        """Host-buffer decode of both error types (qldpc_decode_host, pinned or pageable memory): syn_* are int32 host tensors
+        (shots, words(m)), out_* = (ehat int32 (shots, words(n)), iters int32 (shots,), converged uint8 (shots,)).  The two
+        decodes are independent plans with their own streams and staging buffers; they are issued from two host threads so
+        that the copy-in of one overlaps the kernels of the other and the tail of a chunk of one decode (a few long-running
+        shots keep their SMs) is filled by CTAs of the other."""
+        import threading
+        L = _lib.lib()
+        shots = int(syn_z.shape[0])
+        errs = []
+
+        def work(dec, hs, ho):
+            try:
+                _lib.check(L.qldpc_decode_host(dec.handle, hs.data_ptr(), shots, ho[0].data_ptr(), ho[1].data_ptr(),
+                                               ho[2].data_ptr() if ho[2] is not None else None, None))
+            except Exception as e:          # re-raised in the caller's thread
+                errs.append(e)
+        th = threading.Thread(target=work, args=(self.decZ, syn_x, out_z))
+        th.start()
+        work(self.decX, syn_z, out_x)
+        th.join()
+        if errs:
+            raise errs[0]
+
+
 def simulate_p(Hx: np.ndarray, Hz: np.ndarray, p: float, shots: int = 1000, decType: str = "MS",
                decIterations: int = 99, decSchedule: str = "F", OSDorder: int = -1, rngSeed: Optional[int] = None,
                *, record: Optional[np.ndarray] = None, sampler_kind: str = "host", chunk: int = 1 << 20,
