@@ -182,14 +182,32 @@ __global__ void __launch_bounds__(256) bf_sparse_kernel(GraphDev g, const uint32
 //   variables), which yields the same integers as the reference's recomputation.
 // Shared memory per warp: est bits [nw] | residual bits [mw] | score int32 [n].
 // ---------------------------------------------------------------------------------------------------------
+// TAB16: CSR / CSC copied to shared memory as uint16 once per CTA (every index < 65536); otherwise read through L1.
+template <bool TAB16>
 __global__ void __launch_bounds__(256) ng_decode_kernel(GraphDev g, DecodeIO io)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int per = g.nw + g.mw + g.n;
     uint32_t *eb = reinterpret_cast<uint32_t *>(smem) + (size_t)warp * per;
     uint32_t *rb = eb + g.nw;
     int *score = reinterpret_cast<int *>(rb + g.mw);
+    // per-CTA tables behind the per-warp state: row_ptr [m+1] | col_ptr [n+1] | col_idx [E] | row_idx [E]
+    const int E = g.row_ptr[g.m];
+    uint16_t *t_row_ptr = reinterpret_cast<uint16_t *>(reinterpret_cast<uint32_t *>(smem) + (size_t)nwarps * per);
+    uint16_t *t_col_ptr = t_row_ptr + (g.m + 1);
+    uint16_t *t_col_idx = t_col_ptr + (g.n + 1);
+    uint16_t *t_row_idx = t_col_idx + E;
+    if (TAB16) {
+        for (int i = threadIdx.x; i <= g.m; i += blockDim.x) t_row_ptr[i] = (uint16_t)g.row_ptr[i];
+        for (int i = threadIdx.x; i <= g.n; i += blockDim.x) t_col_ptr[i] = (uint16_t)g.col_ptr[i];
+        for (int i = threadIdx.x; i < E; i += blockDim.x) { t_col_idx[i] = (uint16_t)g.col_idx[i]; t_row_idx[i] = (uint16_t)g.row_idx[i]; }
+        __syncthreads();
+    }
+    auto row_ptr = [&](int i) -> int { return TAB16 ? (int)t_row_ptr[i] : g.row_ptr[i]; };
+    auto col_ptr = [&](int j) -> int { return TAB16 ? (int)t_col_ptr[j] : g.col_ptr[j]; };
+    auto col_idx = [&](int x) -> int { return TAB16 ? (int)t_col_idx[x] : g.col_idx[x]; };
+    auto row_idx = [&](int x) -> int { return TAB16 ? (int)t_row_idx[x] : g.row_idx[x]; };
     const unsigned full = 0xffffffffu;
     for (;;) {
         long long shot = 0;
@@ -203,7 +221,7 @@ __global__ void __launch_bounds__(256) ng_decode_kernel(GraphDev g, DecodeIO io)
         __syncwarp();
         for (int j = lane; j < g.n; j += 32) {
             int sc = 0;
-            for (int x = g.col_ptr[j]; x < g.col_ptr[j + 1]; ++x) sc += get_bit(rb, g.row_idx[x]);
+            for (int x = col_ptr(j); x < col_ptr(j + 1); ++x) sc += get_bit(rb, row_idx(x));
             score[j] = sc;
         }
         __syncwarp();
@@ -220,14 +238,14 @@ __global__ void __launch_bounds__(256) ng_decode_kernel(GraphDev g, DecodeIO io)
             if (wbest == 0) break;                                       // :57-58
             const int v = __reduce_min_sync(full, best == wbest ? arg : 0x7fffffff);   // first maximum (:59)
             if (lane == 0) eb[v >> 5] ^= 1u << (v & 31);                 // :61
-            const int t0 = g.col_ptr[v], t1 = g.col_ptr[v + 1];
+            const int t0 = col_ptr(v), t1 = col_ptr(v + 1);
             for (int x = t0; x < t1; ++x) {                              // :63-64, one check at a time
-                const int ch = g.row_idx[x];
+                const int ch = row_idx(x);
                 const int was = get_bit(rb, ch);
                 const int delta = was ? -1 : 1;
                 __syncwarp();
                 if (lane == 0) rb[ch >> 5] ^= 1u << (ch & 31);
-                for (int y = g.row_ptr[ch] + lane; y < g.row_ptr[ch + 1]; y += 32) score[g.col_idx[y]] += delta;
+                for (int y = row_ptr(ch) + lane; y < row_ptr(ch + 1); y += 32) score[col_idx(y)] += delta;
                 rsum += delta;
                 __syncwarp();
             }

@@ -129,6 +129,7 @@ struct PlanKernels {
     LaneTables lane_tab{};
     bp_kernel_t bp = nullptr;
     const void *bf = nullptr;  // bit-flipping kernel of the plan (dense or sparse formulation)
+    const void *ng = nullptr;  // naive-greedy kernel of the plan (tables in shared memory or through L1)
     int bp_team = 1;           // warps per shot of the sum-product kernel
     bool regular = false;
 };
@@ -572,7 +573,11 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
         p->shots_per_cta = warps;
         p->smem_bytes = per * warps + (bf_sparse ? (((size_t)n + 15) & ~size_t(15)) : 0);
         if (p->smem_bytes > (size_t)kMaxSmemPerCta) return bail(QLDPC_ETOOBIG, "code too large");
-        const void *fn = (const void *)ng_decode_kernel;
+        const bool ng_tab16 = o->dec_type == QLDPC_NG && E < 65536 && m < 65535 && n < 65535;
+        const void *fn = ng_tab16 ? (const void *)ng_decode_kernel<true> : (const void *)ng_decode_kernel<false>;
+        if (ng_tab16) p->smem_bytes = ((p->smem_bytes + 3) & ~size_t(3)) + (size_t)(m + 1 + n + 1 + 2 * E) * 2;
+        if (p->smem_bytes > (size_t)kMaxSmemPerCta) return bail(QLDPC_ETOOBIG, "code too large");
+        pk->ng = fn;
         if (o->dec_type == QLDPC_BF) {
             fn = (const void *)bf_decode_kernel;
             if (bf_sparse) switch (col_words(t.mw) / 4) {
@@ -734,7 +739,11 @@ static int launch_decode(qldpc_plan *p, const uint32_t *syn, int64_t shots, uint
         }
         break;
     case QLDPC_NG:
-        ng_decode_kernel<<<grid, p->threads, p->smem_bytes, st>>>(graph_dev(p), io);
+        {
+            GraphDev gd = graph_dev(p);
+            void *args[] = {&gd, &io};
+            CU_TRY(cudaLaunchKernel(kernels_of(p)->ng, dim3(grid), dim3(p->threads), args, p->smem_bytes, st));
+        }
         break;
     }
     g_launches++;
