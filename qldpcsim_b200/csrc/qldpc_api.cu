@@ -697,7 +697,7 @@ static int launch_decode(qldpc_plan *p, const uint32_t *syn, int64_t shots, uint
             sc.c2v = (float *)sb; sc.S = (float *)(sb + b_c2v); sc.par = (uint32_t *)(sb + b_c2v + b_S);
             sc.eb = (uint32_t *)(sb + b_c2v + b_S + b_par);
             // shots that need more than kLaneIters iterations are deferred to the warp-per-shot kernel (second launch below)
-            constexpr int kLaneIters = 6;
+            static const int kLaneIters = [] { const char *ev = getenv("QLDPC_LANE_ITERS"); const int v = ev ? atoi(ev) : 0; return v > 0 ? v : 6; }();   // tuning knob
             const bool defer = o.max_iter > kLaneIters;
             if (defer) {
                 if ((rc2 = ensure_scratch(p, 4, (size_t)shots * sizeof(int) + 16))) return rc2;
