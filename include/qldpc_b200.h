@@ -80,7 +80,9 @@ int         qldpc_abi_version(void);
 const char *qldpc_last_error(void);
 int         qldpc_words(int32_t nbits);             /* ceil(nbits/32) */
 
-/* Builds the device-resident plan (CSC, slot-major edge tables, per-layer variable lists, launch geometry).
+/* Builds the device-resident plan (CSC, the decoder's shared-memory tables -- for min-sum the variable-major message
+ * layout chosen by the layout planner, for sum-product slot-major edge tables --, per-layer variable lists, bit-packed
+ * rows and columns of H, launch geometry).
  * `device` is a CUDA ordinal. */
 int qldpc_plan_create(const qldpc_graph *graph, const qldpc_opts *opts, int device, qldpc_plan **out);
 int qldpc_plan_destroy(qldpc_plan *plan);

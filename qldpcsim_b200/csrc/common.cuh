@@ -14,7 +14,8 @@ constexpr int kWarp = 32;
 constexpr uint16_t kPad = 0xFFFF;          // padding entry of the slot-major variable table
 constexpr int kMaxSmemPerCta = 227 * 1024; // B200: 227 KB opt-in dynamic shared memory per CTA
 
-// Device view of the graph tables.  All tables live in one uint16 blob that every CTA copies into shared
+// Device view of the graph tables of the SUM-PRODUCT kernel (the min-sum kernel has its own, MsTables in ms_kernel.cuh;
+// m, n, E, mw, nw, nl, dv are filled for every plan).  All tables live in one uint16 blob that every CTA copies into shared
 // memory once; offsets are in uint16 units.  Edge storage is SLOT-MAJOR: the k-th edge (ascending variable)
 // of check i sits at position k*m + i, so that a warp whose lanes hold consecutive checks touches
 // consecutive shared-memory words (no bank conflicts), and -- for circulant-lifted codes -- consecutive

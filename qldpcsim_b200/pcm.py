@@ -11,7 +11,7 @@ PCM compiler (host side): dense parity-check matrix -> what the CUDA library's p
                        README.md:15-22 need; the reference never computes them).
  * `detect_qc`       : recovers (L, base shift matrix) of a circulant-permutation lifted matrix
                        (PCMlibrary.py:129-138, 195-201) so kernels may replace index loads by arithmetic.
-The device-side tables (slot-major edge layout, per-layer variable lists) are derived from the CSR + layers by
+The device-side tables (message layout, check-slot assignment, per-layer variable groups) are derived from the CSR + layers by
 qldpc_plan_create in csrc/ (see include/qldpc_b200.h).
 """
 from __future__ import annotations
