@@ -19,7 +19,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
 def sources():
     out = [SRC, os.path.join(os.path.dirname(HERE), "include", "qldpc_b200.h")]
     d = os.path.join(HERE, "csrc")
-    out += [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith((".cuh", ".cu"))]
+    out += [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith((".cuh", ".cu", ".h", ".cpp"))]
     return out
 
 

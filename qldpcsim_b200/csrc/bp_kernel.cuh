@@ -196,8 +196,7 @@ __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint
                         const int src = __ffs(flips) - 1;
                         flips &= flips - 1;
                         const int jf = __shfl_sync(full, j, src);
-                        const int x = col_ptr[jf] + lane;
-                        if (x < col_ptr[jf + 1]) {
+                        for (int x = col_ptr[jf] + lane; x < col_ptr[jf + 1]; x += 32) {     // columns may hold more than 32 checks
                             const int ch = col_chk[x];
                             const uint32_t bit = 1u << (ch & 31);
                             const uint32_t old = atomicXor(&par[ch >> 5], bit);

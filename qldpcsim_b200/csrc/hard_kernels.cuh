@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) bf_decode_kernel(GraphDev g, int max_iter
 //     own word of e, one warp OR-reduction per residual word).
 // Same integers as the dense kernel above (kept for matrices with more than 1024 checks); ~3.5x fewer instructions.
 // Shared memory per warp: e bits [nw] | r bits [mw] | syndrome bits [mw] | counters uint32 [32*nw] | list uint16 [m rounded to 2].
-// Per CTA (after the warps): column weights uint8 [n].
+// Per CTA (after the warps): column weights uint16 [n] (a column has at most m <= 1024 entries here).
 template <int VH>
 __global__ void __launch_bounds__(256) bf_sparse_kernel(GraphDev g, const uint32_t *__restrict__ hcol, int max_iter, DecodeIO io)
 {
@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(256) bf_sparse_kernel(GraphDev g, const uint32
     uint32_t *sb = rb + g.mw;
     uint32_t *nuc = sb + g.mw;
     uint16_t *list = reinterpret_cast<uint16_t *>(nuc + 32 * g.nw);
-    uint8_t *colw = reinterpret_cast<uint8_t *>(reinterpret_cast<uint32_t *>(smem) + (size_t)nwarps * per);
-    for (int j = threadIdx.x; j < g.n; j += blockDim.x) colw[j] = (uint8_t)min(255, g.col_ptr[j + 1] - g.col_ptr[j]);
+    uint16_t *colw = reinterpret_cast<uint16_t *>(reinterpret_cast<uint32_t *>(smem) + (size_t)nwarps * per);
+    for (int j = threadIdx.x; j < g.n; j += blockDim.x) colw[j] = (uint16_t)(g.col_ptr[j + 1] - g.col_ptr[j]);
     __syncthreads();
     const unsigned full = 0xffffffffu;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -321,6 +321,20 @@ __device__ __forceinline__ bool xor_columns_nonzero(const uint4 *__restrict__ co
     return bad;
 }
 
+// M e + s != 0 (mod 2) row by row through the CSR tables: matrices with more than 1024 checks, whose bit-packed columns do not
+// fit the 128-byte column lines (e, s: global memory, read through L1)
+__device__ __forceinline__ bool rows_parity_nonzero(const GraphDev &g, const uint32_t *e, const uint32_t *syn, int lane)
+{
+    bool bad = false;
+    for (int i = lane; i < g.m; i += 32) {
+        uint32_t par = get_bit(syn, i);
+        for (int x = g.row_ptr[i]; x < g.row_ptr[i + 1]; ++x) par ^= get_bit(e, g.col_idx[x]);
+        bad |= par != 0u;
+    }
+    return __any_sync(0xffffffffu, bad);
+}
+
+// VH: 128-bit loads per column of H (0: row-wise parities, more than 1024 checks); VL: per column of the logical bases
 template <int VH, int VL>
 __global__ void __launch_bounds__(256) classify_kernel(ClassifyArgs a)
 {
@@ -343,8 +357,14 @@ __global__ void __launch_bounds__(256) classify_kernel(ClassifyArgs a)
         }
         const bool exact = !__any_sync(0xffffffffu, diff);
         const bool degen = !exact && !__any_sync(0xffffffffu, touch);
-        const bool fx = xor_columns_nonzero<VH>(reinterpret_cast<const uint4 *>(a.hcol_z), nw, hx, nullptr, a.synz + s * a.gz.mw, a.gz.mw, lane);
-        const bool fz = xor_columns_nonzero<VH>(reinterpret_cast<const uint4 *>(a.hcol_x), nw, hz, nullptr, a.synx + s * a.gx.mw, a.gx.mw, lane);
+        bool fx, fz;
+        if constexpr (VH > 0) {
+            fx = xor_columns_nonzero<VH>(reinterpret_cast<const uint4 *>(a.hcol_z), nw, hx, nullptr, a.synz + s * a.gz.mw, a.gz.mw, lane);
+            fz = xor_columns_nonzero<VH>(reinterpret_cast<const uint4 *>(a.hcol_x), nw, hz, nullptr, a.synx + s * a.gx.mw, a.gx.mw, lane);
+        } else {
+            fx = rows_parity_nonzero(a.gz, hx, a.synz + s * a.gz.mw, lane);
+            fz = rows_parity_nonzero(a.gx, hz, a.synx + s * a.gx.mw, lane);
+        }
         // README classes (README.md:15-22): the residual of a shot whose two syndromes are reproduced lies in the normaliser;
         // it is a stabiliser iff its X part commutes with every logical Z and its Z part with every logical X
         bool logical = false;

@@ -161,7 +161,9 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
     p->opts = *o;
     p->row_ptr.assign(g->row_ptr, g->row_ptr + m + 1);
     p->col_idx.assign(g->col_idx, g->col_idx + E);
-    auto bail = [&](int code, const std::string &msg) { qldpc_plan_destroy(p); return fail(code, msg); };
+    // every early return below (validation, QLDPC_ETOOBIG, any failing CUDA call) releases the half-built plan
+    struct PlanGuard { qldpc_plan *p; ~PlanGuard() { if (p) qldpc_plan_destroy(p); } } guard{p};
+    auto bail = [&](int code, const std::string &msg) { return fail(code, msg); };
 
     // ---- validate CSR, build CSC (ascending check per variable because rows are visited in order)
     int dc = 0;
@@ -220,7 +222,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
     // ---- device copies of CSR / CSC and bit-packed rows
     int rc = 0;
     if ((rc = upload(&p->d_row_ptr, p->row_ptr)) || (rc = upload(&p->d_col_idx, p->col_idx)) ||
-        (rc = upload(&p->d_col_ptr, p->col_ptr)) || (rc = upload(&p->d_row_idx, p->row_idx))) { qldpc_plan_destroy(p); return rc; }
+        (rc = upload(&p->d_col_ptr, p->col_ptr)) || (rc = upload(&p->d_row_idx, p->row_idx))) return rc;
     {
         std::vector<uint32_t> hb((size_t)(m + 1) * t.nw, 0u);     // row m = OR of all rows (column mask)
         for (int i = 0; i < m; ++i)
@@ -229,13 +231,13 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
                 hb[(size_t)i * t.nw + (j >> 5)] |= 1u << (j & 31);
                 hb[(size_t)m * t.nw + (j >> 5)] |= 1u << (j & 31);
             }
-        if ((rc = upload(&p->d_hbits, hb))) { qldpc_plan_destroy(p); return rc; }
+        if ((rc = upload(&p->d_hbits, hb))) return rc;
         const int cwd = kColStride;
         std::vector<uint32_t> hc((size_t)n * cwd, 0u);
         if (t.mw <= 32)
             for (int i = 0; i < m; ++i)
                 for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x) hc[(size_t)p->col_idx[x] * cwd + (i >> 5)] |= 1u << (i & 31);
-        if ((rc = upload(&p->d_hcol, hc))) { qldpc_plan_destroy(p); return rc; }
+        if ((rc = upload(&p->d_hcol, hc))) return rc;
         // GF(2) rank of H (gf2math.py:91-135) by bit-packed elimination on the host; OSD stops its column walk there
         std::vector<uint32_t> w(hb.begin(), hb.begin() + (size_t)m * t.nw);
         int r = 0;
@@ -470,7 +472,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             }
             fn = (const void *)pk->bp;
         }
-        if ((rc = upload(&p->d_blob, b))) { qldpc_plan_destroy(p); return rc; }
+        if ((rc = upload(&p->d_blob, b))) return rc;
         const size_t blob_bytes = is_ms ? (size_t)ms_table_bytes(pk->ms_tab) : (((size_t)t.len * 2 + 15) & ~size_t(15));
         if (!fn) return bail(QLDPC_ETOOBIG, "row weight not supported");
         if (blob_bytes + state > (size_t)kMaxSmemPerCta)
@@ -556,7 +558,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
                 else if (dc_true <= 8 && dv <= 5) pk->ms_lane = ms_lane_kernel<8, 5>;
                 else if (dc_true <= 18 && dv <= 9) pk->ms_lane = ms_lane_kernel<18, 9>;
                 else pk->ms_lane = ms_lane_kernel<32, 16>;
-                if ((rc = upload(&p->d_lane_blob, lb))) { qldpc_plan_destroy(p); return rc; }
+                if ((rc = upload(&p->d_lane_blob, lb))) return rc;
                 CU_TRY(cudaFuncSetAttribute((const void *)pk->ms_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta));
                 p->use_lane = true;
                 p->lane_forced = o->reserved == 2;
@@ -571,7 +573,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
         p->state_bytes = per;
         p->threads = warps * kWarp;
         p->shots_per_cta = warps;
-        p->smem_bytes = per * warps + (bf_sparse ? (((size_t)n + 15) & ~size_t(15)) : 0);
+        p->smem_bytes = per * warps + (bf_sparse ? (((size_t)2 * n + 15) & ~size_t(15)) : 0);
         if (p->smem_bytes > (size_t)kMaxSmemPerCta) return bail(QLDPC_ETOOBIG, "code too large");
         const bool ng_tab16 = o->dec_type == QLDPC_NG && E < 65536 && m < 65535 && n < 65535;
         const void *fn = ng_tab16 ? (const void *)ng_decode_kernel<true> : (const void *)ng_decode_kernel<false>;
@@ -593,6 +595,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, p->threads, p->smem_bytes));
         p->grid = p->sm_count * std::max(1, per_sm);
     }
+    guard.p = nullptr;
     *out = p;
     return QLDPC_OK;
 }
@@ -881,18 +884,18 @@ int qldpc_classify(const qldpc_plan *px, const qldpc_plan *pz, const uint32_t *e
     a.hcol_z = px->d_hcol; a.hcol_x = pz->d_hcol;
     const bool lg = px->d_lcol && pz->d_lcol;
     a.lcol_z = lg ? px->d_lcol : nullptr; a.lcol_x = lg ? pz->d_lcol : nullptr;
-    if (px->tab.mw > 32 || pz->tab.mw > 32) return fail(QLDPC_ETOOBIG, "classification supports up to 1024 checks per matrix");
     a.errx = errx; a.errz = errz; a.ehx = ehx; a.ehz = ehz; a.synz = synz; a.synx = synx; a.itx = itx; a.itz = itz;
     a.shots = shots;
     a.counters = reinterpret_cast<unsigned long long *>(counters);
     const int threads = 256;
     const int grid = (int)std::min<int64_t>((int64_t)px->sm_count * 8, (shots + 7) / 8);
     // VH: 128-bit loads per column of H (both matrices use the wider one), VL: per column of the logical bases (2 or 8)
-    const int vh = col_words(std::max(px->tab.mw, pz->tab.mw)) / 4;
+    const int vh = std::max(px->tab.mw, pz->tab.mw) > 32 ? 0 : col_words(std::max(px->tab.mw, pz->tab.mw)) / 4;   // 0: row-wise (CSR)
     const bool wide = lg && (std::max(px->lkw, pz->lkw) > 8);
     cudaStream_t cst = (cudaStream_t)stream;
 #define QLDPC_CLS(VH) do { if (wide) classify_kernel<VH, 8><<<grid, threads, 0, cst>>>(a); else classify_kernel<VH, 2><<<grid, threads, 0, cst>>>(a); } while (0)
     switch (vh) {
+    case 0: QLDPC_CLS(0); break;
     case 1: QLDPC_CLS(1); break;
     case 2: QLDPC_CLS(2); break;
     case 4: QLDPC_CLS(4); break;

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
-"""Large sum-product golden: the UNMODIFIED reference's BP_decoder (decoders.py:189-290) on 1600 X-error decodes of LP118_0
-(flooding, 100 iterations, depolarizing p = 0.05, sampler seed 777), called exactly as simulator.py:281 does.
+"""Large sum-product goldens: the UNMODIFIED reference's BP_decoder (decoders.py:189-290) on 1600 X-error decodes of LP118_0
+(flooding, 100 iterations, sampler seed 777), called exactly as simulator.py:281 does, at one depolarizing probability of
+BASELINE config 2's sweep per file (p = 0.05 by default; 0.02 and 0.10 are the ends that are also committed).
 
-    python tests/golden/make_bp_golden.py        (needs /root/reference; ~40 s on 8 cores)
+    python tests/golden/make_bp_golden.py [P]    (needs /root/reference; ~40 s on 8 cores at p = 0.05, ~5 min at p = 0.10)
 
 Why a separate, larger fixture: BP parity is statistical.  On this configuration 1.4 % of the decodes do not converge,
 their final hard decision after 100 iterations is chaotic in the last bits of tanh / arctanh, and NumPy's SIMD routines,
@@ -23,7 +24,7 @@ sys.path.insert(0, ROOT)
 from oracle import oracle, ref_loader  # noqa: E402
 from qldpcsim_b200 import bitpack, pcmlibrary, sampler  # noqa: E402
 
-CODE, P, SHOTS, ITERS, SEED = "LP118_0", 0.05, 1600, 100, 777
+CODE, P, SHOTS, ITERS, SEED = "LP118_0", (float(sys.argv[1]) if len(sys.argv) > 1 else 0.05), 1600, 100, 777
 Hx, Hz = [(h % 2).astype(np.int8) for h in pcmlibrary.by_name(CODE)]
 rec = sampler.sample_record(Hx, Hz, P, SHOTS, seed=SEED)
 sy_z, _, _, _ = oracle.split_record(rec, Hz.shape[0], Hx.shape[0], Hx.shape[1])
@@ -44,6 +45,6 @@ if __name__ == "__main__":
     with mp.Pool(os.cpu_count()) as pool:
         res = pool.map(work, [(i, min(SHOTS, i + 25)) for i in range(0, SHOTS, 25)])
     ref = [x for c in res for x in c]
-    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "big_LP118_0_BP_F_p05_X.npz"), code=CODE, decType="BP",
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), f"big_LP118_0_BP_F_p{round(P * 100):02d}_X.npz"), code=CODE, decType="BP",
                         sched="F", p=P, shots=SHOTS, decIterations=ITERS, seed=SEED, syn=bitpack.pack_rows(sy_z.astype(bool)),
                         e=bitpack.pack_rows(np.array([r[0] for r in ref]).astype(bool)), it=np.array([r[1] for r in ref], np.int32))

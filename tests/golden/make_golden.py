@@ -69,6 +69,11 @@ CASES = [
     ("LP118_0_MS_F_p05", "LP118_0", "MS", "F", 0.05, 48, 50, -1, False),
     ("LP118_0_BP_F_p05", "LP118_0", "BP", "F", 0.05, 16, 100, -1, False),
     ("LP118_0_MS_L_OSD0_p10", "LP118_0", "MS", "L", 0.10, 8, 5, 0, False),
+    # OSD at BASELINE config-3 size (n > 992: the two-words-per-lane OSD kernel); ~25 s per unconverged decode in the reference
+    ("LP118_2_MS_S_OSD0_p05", "LP118_2", "MS", "S", 0.05, 6, 2, 0, False),
+    ("T_MS_L_OSD0_p05", "T", "MS", "L", 0.05, 6, 2, 0, False),
+    # order 10 (BASELINE config 3's order) where the reference can afford its 1024 REF calls per decode
+    ("LP04_0_MS_L_OSD10_p10", "LP04_0", "MS", "L", 0.10, 12, 8, 10, False),
     ("LP118_1_MS_L_p05", "LP118_1", "MS", "L", 0.05, 24, 50, -1, False),
     ("LP118_2_MS_L_p05", "LP118_2", "MS", "L", 0.05, 16, 50, -1, False),
     ("LP118_2_MS_S_p05", "LP118_2", "MS", "S", 0.05, 4, 50, -1, False),

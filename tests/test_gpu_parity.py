@@ -202,6 +202,64 @@ def test_against_oracle(code, decType, sched, p, shots, iters, cuda_device):
         assert abs(q - q_ref) <= half
 
 
+# ---------------------------------------------------------------------------------------------------------
+# OSD at BASELINE-config size: n > 992 columns runs osd_kernel<2> (two words per lane), which none of the reference
+# goldens small enough to generate in bulk reaches.  The oracle (orc_osd, pinned on the reference goldens incl. the
+# LP118_2 / Tanner ones) orders columns like the library (stable), so EVERY shot must be bit-exact, ties included.
+# ---------------------------------------------------------------------------------------------------------
+OSD_BIG_CASES = [
+    # code, sched, p, shots, iters, order, min unconverged decodes (X + Z)
+    ("LP118_2", "S", 0.05, 700, 3, 0, 200),
+    ("LP118_2", "S", 0.05, 700, 3, 1, 200),
+    ("LP118_2", "S", 0.05, 700, 3, 10, 200),
+    ("T", "L", 0.05, 700, 3, 0, 200),
+    ("T", "L", 0.05, 700, 3, 1, 200),
+    ("T", "L", 0.05, 700, 3, 10, 200),
+    ("LP118_2", "S", 0.05, 70000, 50, 10, 100),     # BASELINE config 3 as stated: MS serial, 50 iterations, OSD order 10
+]
+
+
+@pytest.mark.parametrize("code,sched,p,shots,iters,order,min_unconv", OSD_BIG_CASES)
+def test_osd_config3_size_against_oracle(code, sched, p, shots, iters, order, min_unconv, cuda_device):
+    from oracle import oracle
+    from qldpcsim_b200 import bitpack, pcmlibrary, sampler, simulator
+    Hx, Hz = [(h % 2).astype(np.int8) for h in pcmlibrary.by_name(code)]
+    n = Hx.shape[1]
+    assert n > 992, "the case must run the two-words-per-lane OSD kernel"
+    rec = sampler.sample_record(Hx, Hz, p, shots, seed=2468)
+    want = oracle.simulate_p(Hx, Hz, rec, p, decType="MS", decIterations=iters, decSchedule=sched, OSDorder=order, details=True)
+    got = simulator.simulate_p(Hx, Hz, p, shots=shots, decType="MS", decIterations=iters, decSchedule=sched, OSDorder=order,
+                               record=rec, details=True)
+    wd, gd = want["_details"], got["_details"]
+    unconv = int((~wd["convX"]).sum() + (~wd["convZ"]).sum())
+    assert unconv >= min_unconv, f"only {unconv} unconverged decodes reach OSD"
+    eX = bitpack.unpack_rows(gd["eX"].view(np.uint32), n)
+    eZ = bitpack.unpack_rows(gd["eZ"].view(np.uint32), n)
+    assert np.array_equal(gd["itX"], wd["itX"]) and np.array_equal(gd["itZ"], wd["itZ"])
+    badX, badZ = np.nonzero((eX != wd["eX"]).any(axis=1))[0], np.nonzero((eZ != wd["eZ"]).any(axis=1))[0]
+    assert len(badX) == 0 and len(badZ) == 0, f"OSD-{order} differs from the oracle on shots X {badX[:5]} Z {badZ[:5]}"
+    # every shot reproduces its syndrome after OSD (rank(H) basis columns always exist)
+    assert got["DecFailures_X"] == 0 and got["DecFailures_Z"] == 0
+    assert got["decSuccessExact"] == want["decSuccessExact"]
+    if order >= 2:
+        # App. B-8: the reference's order loop aliases its buffers, so order >= 2 returns the order-0 vector
+        got0 = simulator.simulate_p(Hx, Hz, p, shots=min(shots, 2000), decType="MS", decIterations=iters, decSchedule=sched,
+                                    OSDorder=0, record=rec[:2000], details=True)["_details"]
+        assert np.array_equal(got0["eX"], gd["eX"][:2000]) and np.array_equal(got0["eZ"], gd["eZ"][:2000])
+
+
+@pytest.mark.parametrize("code,rank_x,rank_z", [("steane", 3, 3), ("shor", 2, 6), ("LP04_0", 78, 78), ("LP118_0", 232, 232),
+                                                ("LP118_2", 442, 442), ("T", 457, 457), ("bicycle", 55, 55)])
+def test_plan_rank_matches_survey(code, rank_x, rank_z, cuda_device):
+    """GF(2) rank computed at plan creation (gf2math.py:91-135) = SURVEY.md App. C; OSD stops its column walk there."""
+    from oracle import oracle
+    from qldpcsim_b200 import pcmlibrary
+    from qldpcsim_b200.decoders import Decoder
+    Hx, Hz = [(h % 2).astype(np.int8) for h in pcmlibrary.by_name(code)]
+    assert Decoder(Hx, "NG").info()["rank"] == rank_x == oracle.gf2_rank(Hx)
+    assert Decoder(Hz, "NG").info()["rank"] == rank_z == oracle.gf2_rank(Hz)
+
+
 def test_reference_signature_functions(cuda_device):
     """The five per-shot functions keep the reference's signatures, return types and dtypes."""
     from qldpcsim_b200 import decoders as D
@@ -248,11 +306,9 @@ def _philox_host(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
-def test_device_sampler_matches_host_restatement(cuda_device):
+def _check_device_sampler(Hx, Hz, p, seed, first, shots):
     """qldpc_sample against a pure-Python restatement of its definition (Philox4x32-10, thresholds k p/3 2^32)."""
-    from qldpcsim_b200 import bitpack, pcmlibrary, simulator
-    Hx, Hz = pcmlibrary.by_name("LP04_0")
-    p, seed, first, shots = 0.07, 0x1234ABCD5678, 1000, 6
+    from qldpcsim_b200 import bitpack, simulator
     pipe = simulator.Pipeline(Hx, Hz, p, "NG")
     synz, synx, errx, errz = [t.cpu().numpy().view(np.uint32) for t in pipe.sample_device(shots, seed, first)]
     n = Hx.shape[1]
@@ -267,8 +323,44 @@ def test_device_sampler_matches_host_restatement(cuda_device):
             X, Y, Z = r < thr[0], thr[0] <= r < thr[1], thr[1] <= r < thr[2]
             eX[s, q], eZ[s, q] = X or Y, Z or Y
     assert np.array_equal(bitpack.unpack_rows(errx, n), eX) and np.array_equal(bitpack.unpack_rows(errz, n), eZ)
-    assert np.array_equal(bitpack.unpack_rows(synz, Hz.shape[0]), (eX @ Hz.T) % 2)
-    assert np.array_equal(bitpack.unpack_rows(synx, Hx.shape[0]), (eZ @ Hx.T) % 2)
+    assert np.array_equal(bitpack.unpack_rows(synz, Hz.shape[0]), (eX.astype(np.int64) @ Hz.T.astype(np.int64)) % 2)
+    assert np.array_equal(bitpack.unpack_rows(synx, Hx.shape[0]), (eZ.astype(np.int64) @ Hx.T.astype(np.int64)) % 2)
+
+
+def test_device_sampler_matches_host_restatement(cuda_device):
+    from qldpcsim_b200 import pcmlibrary
+    Hx, Hz = pcmlibrary.by_name("LP04_0")
+    _check_device_sampler(Hx, Hz, 0.07, 0x1234ABCD5678, 1000, 6)
+
+
+def big_sparse_matrix(seed=5, m=2200, n=4000, rw=30):
+    """Synthetic matrix beyond the sizes of the reference's library: more than 1024 checks (row-wise sampler / classifier,
+    dense bit-flipping kernel) and more than 65535 edges (naive-greedy tables read through L1 instead of shared memory)."""
+    rng = np.random.default_rng(seed)
+    H = np.zeros((m, n), np.int8)
+    for i in range(m):
+        H[i, rng.choice(n, rw, replace=False)] = 1
+    return H
+
+
+def test_more_than_1024_checks(cuda_device):
+    from oracle import oracle
+    from qldpcsim_b200 import bitpack, sampler, simulator
+    Hx, Hz = big_sparse_matrix(5), big_sparse_matrix(6)
+    n = Hx.shape[1]
+    _check_device_sampler(Hx, Hz, 0.01, 0xBEEF, 123456789012, 2)                       # sample_kernel<0>
+    shots, p = 40, 0.004
+    rec = sampler.sample_record(Hx, Hz, p, shots, seed=31)
+    for dt in ("NG", "BF"):                                                             # ng_decode_kernel<false>, bf_decode_kernel
+        want = oracle.simulate_p(Hx, Hz, rec, p, decType=dt, details=True)
+        got = simulator.simulate_p(Hx, Hz, p, shots=shots, decType=dt, record=rec, details=True)     # classify_kernel<0, .>
+        eX = bitpack.unpack_rows(got["_details"]["eX"].view(np.uint32), n)
+        eZ = bitpack.unpack_rows(got["_details"]["eZ"].view(np.uint32), n)
+        assert np.array_equal(eX, want["_details"]["eX"]) and np.array_equal(eZ, want["_details"]["eZ"]), dt
+        assert np.array_equal(got["_details"]["itX"], want["_details"]["itX"]), dt
+        for k in ("DecFailures_X", "DecFailures_Z", "decSuccessExact", "decSuccessDegen"):
+            assert got[k] == want[k], (dt, k)
+        assert 0 < want["DecFailures_X"] + want["DecFailures_Z"] or dt == "NG"
 
 
 def test_device_sampler_statistics_and_sharding(cuda_device):
