@@ -71,7 +71,7 @@ typedef struct {
     double  beta;               /* MS normalisation (decoders.py:115), 0.75 in the driver               */
     double  eps;                /* BP clamp shift (decoders.py:195, :257-258)                           */
     int32_t osd_order;          /* OSDorder (decoders.py:116, :194); < 0 disables                       */
-    int32_t reserved;           /* min-sum kernel choice: 0 automatic, 1 warp-per-shot, 2 lane-per-shot           */
+    int32_t reserved;           /* min-sum: 0 automatic, 1 never merge runs of disjoint layers into one step (A/B) */
 } qldpc_opts;
 
 typedef struct qldpc_plan qldpc_plan;
@@ -89,9 +89,10 @@ int qldpc_plan_destroy(qldpc_plan *plan);
 
 /* Plan introspection: what = 0 m, 1 n, 2 nnz, 3 n_layers, 4 CTAs launched, 5 threads per CTA,
  * 6 dynamic shared memory bytes per CTA, 7 shots resident per CTA, 8 max row weight, 9 max column weight,
- * 10 GF(2) rank of H (gf2math.rank, gf2math.py:91-135), 11 whether the lane-per-shot min-sum kernel is used,
+ * 10 GF(2) rank of H (gf2math.rank, gf2math.py:91-135), 11 reserved (0),
  * 12 / 13 shared-memory wavefronts per iteration modelled by the min-sum layout planner / its conflict-free bound,
- * 14 bytes of shared-memory state per shot, 15 number of attached logical operators. */
+ * 14 bytes of shared-memory state per shot, 15 number of attached logical operators, 16 steps per iteration of the min-sum
+ * kernel (< n_layers when runs of layers with disjoint variable sets were merged into one step), 17 warps per shot. */
 int64_t qldpc_plan_info(const qldpc_plan *plan, int what);
 
 /* Decode `shots` syndromes.  Replaces the per-shot calls NG_decoder / BF_decoder / MS_decoder / BP_decoder

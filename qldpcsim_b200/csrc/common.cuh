@@ -57,15 +57,6 @@ struct DecodeIO {
     int *fail_shot;          // [fail_cap]
     double *fail_llr;        // [fail_cap][n]
     int fail_cap;
-    // indirection (second pass of the lane-per-shot min-sum path): when shot_list is set, dispenser position k stands for
-    // shot shot_list[k] and the number of positions is *list_len (device memory); otherwise position k is shot k of `shots`
-    const int *shot_list;
-    const int *list_len;
-    // lane-per-shot kernel only: shots still running after `defer_iters` (< max_iter) iterations are abandoned and appended
-    // here (position counter + list) for a warp-per-shot pass that decodes them from scratch
-    int *defer_count;
-    int *defer_list;
-    int defer_iters;
 };
 
 struct MsConst {
@@ -96,11 +87,6 @@ struct qldpc_plan {
     // host copies of the graph (CSR / CSC) for the kernels that want int32 tables in global memory
     std::vector<int32_t> row_ptr, col_idx, col_ptr, row_idx, layer_ptr, layer_chk;
     uint16_t *d_blob = nullptr;
-    uint16_t *d_lane_blob = nullptr;   // tables of the lane-per-shot min-sum kernel (serial-like schedules)
-    bool use_lane = false;         // lane kernel available for this plan
-    bool lane_forced = false;      // opts.reserved == 2: use it for every batch size
-    int lane_grid = 0;
-    size_t lane_smem = 0;
     int32_t *d_row_ptr = nullptr, *d_col_idx = nullptr, *d_col_ptr = nullptr, *d_row_idx = nullptr;
     uint32_t *d_hbits = nullptr;   // [m][nw] bit-packed rows of H (OSD, sampler, classification)
     uint32_t *d_hcol = nullptr;    // [n][kColStride] bit-packed columns of H (syndrome of a sparse vector), zero padded

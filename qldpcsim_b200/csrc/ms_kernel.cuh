@@ -32,6 +32,16 @@
 //   * convergence is tested after every layer step (decoders.py:175-176) on an incrementally maintained count
 //     of unsatisfied checks: a flipped decision toggles the parity bits of its checks (shared-memory atomics,
 //     rare) and adds +-1 per toggled bit;
+//   * MERGED STEPS (SPEC instances).  Consecutive layers whose variable sets are pairwise disjoint -- the single-check layers of
+//     the serial schedule inside one circulant block row, simulator.py:228-236 'S' -- read nothing that an earlier layer of the
+//     run writes, so their check phases and variable phases are executed as ONE step (the plan builder forms the runs).  What
+//     remains sequential is the reference's convergence test after every layer (decoders.py:175-176): the step must stop after
+//     the first sub-layer whose updates satisfy all checks, with the later sub-layers' posteriors untouched.  The variable phase
+//     of a merged step therefore keeps the new sums in registers, counts the flipped decisions F, and
+//       - if unsat > dv_max * F no prefix of the run can reach zero unsatisfied checks: everything is committed at once;
+//       - otherwise (a few steps per decode, near convergence) the flips are committed sub-layer by sub-layer in order, testing
+//         the count after each, and on convergence only the sums of the sub-layers up to that one are stored.
+//     Results are bit-identical to running the layers one by one; LP118_2 serial costs 15 steps per iteration instead of 450;
 //   * control flow is kept warp-uniform everywhere (padded lists, selects instead of branches, cooperative flip
 //     handling): a lane-divergent loop was measured to split warps into halves that never reconverged.
 // Shared memory is addressed with explicit 32-bit shared-window addresses (ld.shared / st.shared) so that the
@@ -61,11 +71,13 @@ struct MsTables {
     int c2v_words;       // words of the per-shot c2v array (multiple of 32: every region starts on bank 0)
     int off_chk;         // u32 [dc*ms]   lo16 = 4*j' (byte offset of S_j'), hi16 = byte offset of the edge's c2v word.  Slots past the
                          //               end of a short row hold a PADDING EDGE: S entry n+1 (always +inf) and the scratch word S[n+2]
-    int off_layer;       // u16 [nl][8]   16-byte record per layer: {qb, qe (range in layer_chk), lanes per check (1, 2, 4 or 8),
-                         //               vb, ve (range in lvar, 32-bit entries, multiples of 32), 1 if the second sub-group of the
-                         //               layer's LAST pair-trip is empty (a single-variable trip is run instead), 0, 0}
+    int off_layer;       // u16 [nl][8]   16-byte record per step (a layer, or a merged run of layers): {qb, qe (range in layer_chk),
+                         //               lanes per check (1, 2, 4 or 8), vb, ve (range in lvar, 32-bit entries, multiples of 32), 1 if
+                         //               the second sub-group of the step's LAST pair-trip is empty (a single-variable trip is run
+                         //               instead), number of sub-layers of a merged step (0: plain layer), 0}
     int off_layer_chk;   // u16 [...]     check indices, layer by layer
     int off_lvar;        // u32 [...]     lo16 = 4*j'_a, hi16 = 4*j'_b: the two variables of (trip, lane); dummy = 4*n
+    int off_lsub;        // u16 [...]     parallel to lvar: lo8 / hi8 = sub-layer (within its merged step) of variable a / b
     int off_col_ptr;     // u16 [n+2]     CSC pointers in the renumbering (variable n: empty)
     int off_col_chk;     // u16 [E]       checks of j', ascending
     int off_rowpar;      // u32 [mw]      parity of the row weights as bit words
@@ -83,7 +95,8 @@ struct MsSmemLayout {
                    // scratch c2v word of the padding edges
     int off_par;   // uint32 [mw]
     int off_syn;   // uint32 [mw]
-    int off_team;  // 16 bytes: shot mailbox (int64) + unsatisfied-check count (int32) of a multi-warp team
+    int off_team;  // 16 bytes: shot mailbox (int64; bytes 0..3 double as the sub-layer mask of a merged step) + unsatisfied-check
+                   // count (int32) + flip count of a merged step (int32) of a multi-warp team
     int zero_words;
     int bytes;     // multiple of 128: S_j' and every c2v word of j' sit on bank j' mod 32
 };
@@ -285,8 +298,8 @@ __device__ __forceinline__ void ms_var_update4(uint32_t e0, uint32_t e1, int lan
 
 // W: warps per shot ("team", see below), MAXW: warps per CTA the instance is compiled for (launch bound), DC: instantiated row weight (shorter rows are filled with
 // padding edges), DV: instantiated column weight, DMIN: number of
-// leading regions that hold every variable (0 = guard all).
-template <int DC, int DV, int DMIN, int MAXW, int W>
+// leading regions that hold every variable (0 = guard all), SPEC: the plan holds merged steps (see the header).
+template <int DC, int DV, int DMIN, int MAXW, int W, bool SPEC>
 __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, const uint16_t *__restrict__ blob, MsConst c, DecodeIO io)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -326,20 +339,17 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
     A.par = wbase + lay.off_par;
     A.syn = wbase + lay.off_syn;
     A.m4 = 4u * t.ms;
-    const uint32_t layer_rec = tab + 2u * t.off_layer, lvar = tab + 2u * t.off_lvar;
+    const uint32_t layer_rec = tab + 2u * t.off_layer, lvar = tab + 2u * t.off_lvar, lsub = tab + 2u * t.off_lsub;
     const uint32_t rowpar = tab + 2u * t.off_rowpar, unperm = tab + 2u * t.off_unperm;
     const int n = t.n;
     const uint32_t n4 = 4u * (uint32_t)n;
     const float Tf = c.Tf;
     const bool init_bit = 0.0f < Tf;                    // decision of a variable whose sum is still 0 (only if L < 0)
 
-    const long long n_pos = io.shot_list ? (long long)*io.list_len : io.shots;
     for (;;) {
         long long shot = 0;
         if (tl == 0) {
             shot = (long long)atomicAdd(io.work_counter, 1ull);
-            if (io.shot_list && shot < n_pos) shot = io.shot_list[shot];
-            else if (io.shot_list) shot = -1;
             if constexpr (W > 1) asm volatile("st.shared.u64 [%0], %1;" :: "r"(team_box), "l"(shot) : "memory");
         }
         if constexpr (W == 1) shot = __shfl_sync(full, shot, 0);
@@ -347,13 +357,16 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
             team_sync();
             asm volatile("ld.shared.u64 %0, [%1];" : "=l"(shot) : "r"(team_box) : "memory");
         }
-        if (shot < 0 || shot >= io.shots) break;
+        if (shot >= io.shots) break;
 
         // ---- initial state: c2v = 0 (decoders.py:150), S = 0, residual = syndrome (+ H.1 if the all-zero sums decide 1)
         for (int i = tl * 4; i < lay.zero_words; i += 4 * TT)
             asm volatile("st.shared.v4.f32 [%0], {%1,%1,%1,%1};" :: "r"(A.c2v + 4u * i), "f"(0.0f) : "memory");
         team_sync();
-        if (tl == 0) sst_u32(A.S + n4 + 4u, 0x7f800000u);              // S[n+1] = +inf: the padding edges
+        if (tl == 0) {
+            sst_u32(A.S + n4 + 4u, 0x7f800000u);                         // S[n+1] = +inf: the padding edges
+            if constexpr (SPEC && W > 1) { sst_u32(team_box, 0u); sst_u32(team_box + 12u, 0u); }   // exchange words of the merged steps
+        }
         int unsat = 0;
         if (sub == 0) {
             for (int i = lane; i < t.mw; i += 32) {
@@ -407,8 +420,91 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
                 // ---------------- variable-node phase (decoders.py:172-174) on the variables whose sums changed.  Every
                 // lane runs the same number of trips (lists are padded to whole trips with the dummy variable n).
                 const int vb = r1 >> 16, ve = r2 & 0xffffu;
+                const int P = (ve - vb) >> 5;                                  // pair-trips of the step
+                if (SPEC && (r3 & 0xffffu)) {
+                    // ---------------- merged step: at most one quad trip per warp (the plan builder caps the run at 128 W
+                    // variables); sums stay in registers until it is known how far the run may be committed
+                    const int p0 = 2 * sub;
+                    const bool h0 = p0 < P, h1 = p0 + 1 < P;                   // warp-uniform
+                    const uint32_t q0 = (uint32_t)(vb + 32 * p0 + lane);
+                    const uint32_t dummy = n4 | (n4 << 16);
+                    const uint32_t e0 = h0 ? sld_u32(lvar + 4u * q0) : dummy, e1 = h1 ? sld_u32(lvar + 4u * q0 + 128u) : dummy;
+                    const uint32_t j4[4] = {e0 & 0xffffu, e0 >> 16, e1 & 0xffffu, e1 >> 16};
+                    float s_old[4], s_new[4];
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) s_old[v] = sld_f32(A.S + j4[v]);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) s_new[v] = ms_colsum<DV, DMIN>(A.c2v + j4[v], j4[v], t);
+                    uint32_t f[4];
+                    int F = 0;
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        f[v] = __ballot_sync(full, (s_new[v] < Tf) != (s_old[v] < Tf));      // hard decision flipped (:173-174)
+                        F += __popc(f[v]);
+                    }
+                    uint32_t ks0 = 0, ks1 = 0, kmask = 0;                      // sub-layers of my variables; sub-layers that hold flips
+                    if (F) {
+                        ks0 = h0 ? sld_u16(lsub + 2u * q0) : 0u;
+                        ks1 = h1 ? sld_u16(lsub + 2u * q0 + 64u) : 0u;
+                        const uint32_t kk[4] = {ks0 & 0xffu, ks0 >> 8, ks1 & 0xffu, ks1 >> 8};
+                        uint32_t mine = 0;
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) mine |= ((f[v] >> lane) & 1u) << kk[v];
+                        kmask = __reduce_or_sync(full, mine);
+                    }
+                    int Ft = F;
+                    if constexpr (W > 1) {
+                        if (lane == 0 && F) {
+                            asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(team_box + 12u), "r"(F) : "memory");
+                            asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(team_box), "r"(kmask) : "memory");
+                        }
+                        team_sync();
+                        Ft = (int)sld_u32(team_box + 12u);
+                        kmask = sld_u32(team_box);
+                    }
+                    if (unsat > t.dv * Ft) {
+                        // no prefix of the run can satisfy every check (a flip toggles at most dv of them): commit everything
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) sst_f32(A.S + j4[v], s_new[v]);
+                        int delta = 0;
+                        if (F) {
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) ms_apply_flips(f[v], j4[v], lane, A, delta);
+                        }
+                        settle(delta);
+                    } else {
+                        // commit sub-layer by sub-layer, testing after each one (decoders.py:175-176)
+                        if (!F) {
+                            ks0 = h0 ? sld_u16(lsub + 2u * q0) : 0u;
+                            ks1 = h1 ? sld_u16(lsub + 2u * q0 + 64u) : 0u;
+                        }
+                        const uint32_t kk[4] = {ks0 & 0xffu, ks0 >> 8, ks1 & 0xffu, ks1 >> 8};
+                        uint32_t kconv = 64u;
+                        while (kmask) {
+                            const uint32_t k = (uint32_t)__ffs(kmask) - 1u;
+                            kmask &= kmask - 1u;
+                            int delta = 0;
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) {
+                                const uint32_t mk = __ballot_sync(full, ((f[v] >> lane) & 1u) && kk[v] == k);
+                                ms_apply_flips(mk, j4[v], lane, A, delta);
+                            }
+                            settle(delta);
+                            if constexpr (W > 1) team_sync();              // every warp has read the count before the next round adds to it
+                            if (unsat == 0) { kconv = k; break; }
+                        }
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) if (kk[v] <= kconv) sst_f32(A.S + j4[v], s_new[v]);
+                        team_sync();
+                    }
+                    if constexpr (W > 1) {
+                        // the exchange words are next touched after the barrier that follows the next check phase
+                        if (tl == 0 && Ft) { sst_u32(team_box, 0u); sst_u32(team_box + 12u, 0u); }
+                    }
+                    if (unsat == 0) { converged = true; break; }
+                    continue;
+                }
                 int delta = 0;
-                const int P = (ve - vb) >> 5;                                  // pair-trips of the layer; quad trips go round-robin to the warps
                 for (int p = 2 * sub; p + 1 < P; p += 2 * W) {
                     const int q = vb + 32 * p + lane;
                     ms_var_update4<DV, DMIN>(sld_u32(lvar + 4u * q), sld_u32(lvar + 4u * q + 128u), lane, A, t, Tf, delta);

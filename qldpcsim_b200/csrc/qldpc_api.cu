@@ -11,7 +11,6 @@
 #include "common.cuh"
 #include "hard_kernels.cuh"
 #include "ms_kernel.cuh"
-#include "ms_lane_kernel.cuh"
 #include "ms_plan.h"
 #include "osd_kernel.cuh"
 #include "sampler_kernel.cuh"
@@ -71,23 +70,27 @@ typedef void (*ms_kernel_t)(MsTables, const uint16_t *, MsConst, DecodeIO);
 // (the lifted-product / Tanner codes have column weights 3..5), DV for the others (column-regular codes such as bicycle).
 constexpr int ms_fast_dmin(int dv_inst) { return dv_inst <= 5 ? 3 : (dv_inst <= 9 ? dv_inst : 0); }
 
-template <int DC, int MAXW, int W>
+template <int DC, int MAXW, int W, bool SPEC>
 ms_kernel_t ms_pick_dv(int dv_inst, bool fast)
 {
     switch (dv_inst) {
-    case 4: return fast ? (ms_kernel_t)ms_decode_kernel<DC, 4, ms_fast_dmin(4), MAXW, W> : (ms_kernel_t)ms_decode_kernel<DC, 4, 0, MAXW, W>;
-    case 5: return fast ? (ms_kernel_t)ms_decode_kernel<DC, 5, ms_fast_dmin(5), MAXW, W> : (ms_kernel_t)ms_decode_kernel<DC, 5, 0, MAXW, W>;
-    case 9: return fast ? (ms_kernel_t)ms_decode_kernel<DC, 9, ms_fast_dmin(9), MAXW, W> : (ms_kernel_t)ms_decode_kernel<DC, 9, 0, MAXW, W>;
-    case 16: return (ms_kernel_t)ms_decode_kernel<DC, 16, 0, MAXW, W>;
+    case 4: return fast ? (ms_kernel_t)ms_decode_kernel<DC, 4, ms_fast_dmin(4), MAXW, W, SPEC> : (ms_kernel_t)ms_decode_kernel<DC, 4, 0, MAXW, W, SPEC>;
+    case 5: return fast ? (ms_kernel_t)ms_decode_kernel<DC, 5, ms_fast_dmin(5), MAXW, W, SPEC> : (ms_kernel_t)ms_decode_kernel<DC, 5, 0, MAXW, W, SPEC>;
+    case 9: return fast ? (ms_kernel_t)ms_decode_kernel<DC, 9, ms_fast_dmin(9), MAXW, W, SPEC> : (ms_kernel_t)ms_decode_kernel<DC, 9, 0, MAXW, W, SPEC>;
+    case 16: return (ms_kernel_t)ms_decode_kernel<DC, 16, 0, MAXW, W, SPEC>;
     }
     return nullptr;
 }
 
+// merged steps (SPEC instances, see ms_kernel.cuh) exist for the row-weight classes 4, 8 and 16
+inline bool ms_spec_available(int dc_inst) { return dc_inst == 4 || dc_inst == 8 || dc_inst == 16; }
+
 // Instantiated shapes: row weight <= 4 / 8 / 16 / 24 / 32 (multiples of every lane split; shorter rows get padding edges),
 // column weight <= 4 / 5 / 9 / 16.  `full_regions` = number of leading regions that hold every variable; *dmin receives the
 // DMIN of the chosen kernel.
-// variant: 0 = 24 warps per CTA, 1 = 32 warps per CTA (row-weight classes 4 and 8), 2 = teams of two warps per shot (class 8)
-ms_kernel_t ms_select(int dc, int dv, int full_regions, int variant, int *dc_inst, int *dv_inst, int *dmin)
+// variant: 0 = 24 warps per CTA, 1 = 32 warps per CTA (row-weight classes 4 and 8), 2 = teams of two warps per shot (class 8);
+// spec: the plan holds merged steps (variants 0 and 2 only)
+ms_kernel_t ms_select(int dc, int dv, int full_regions, int variant, bool spec, int *dc_inst, int *dv_inst, int *dmin)
 {
     static const int dcs[] = {4, 8, 16, 24, 32}, dvs[] = {4, 5, 9, 16};
     int pc = 0, pv = 0;
@@ -98,12 +101,20 @@ ms_kernel_t ms_select(int dc, int dv, int full_regions, int variant, int *dc_ins
     const int fd = ms_fast_dmin(pv);
     const bool fast = fd > 0 && full_regions >= fd;
     *dmin = fast ? fd : 0;
+    if (spec) {
+        switch (pc) {
+        case 4: return ms_pick_dv<4, kMsWarps, 1, true>(pv, fast);
+        case 8: return variant == 2 ? ms_pick_dv<8, kMsWarps, 2, true>(pv, fast) : ms_pick_dv<8, kMsWarps, 1, true>(pv, fast);
+        case 16: return ms_pick_dv<16, kMsWarps, 1, true>(pv, fast);
+        }
+        return nullptr;
+    }
     switch (pc) {
-    case 4: return variant == 1 ? ms_pick_dv<4, kMsWarpsBig, 1>(pv, fast) : ms_pick_dv<4, kMsWarps, 1>(pv, fast);
-    case 8: return variant == 1 ? ms_pick_dv<8, kMsWarpsBig, 1>(pv, fast) : (variant == 2 ? ms_pick_dv<8, kMsWarps, 2>(pv, fast) : ms_pick_dv<8, kMsWarps, 1>(pv, fast));
-    case 16: return ms_pick_dv<16, kMsWarps, 1>(pv, fast);
-    case 24: return ms_pick_dv<24, kMsWarps, 1>(pv, fast);
-    case 32: return ms_pick_dv<32, kMsWarps, 1>(pv, fast);
+    case 4: return variant == 1 ? ms_pick_dv<4, kMsWarpsBig, 1, false>(pv, fast) : ms_pick_dv<4, kMsWarps, 1, false>(pv, fast);
+    case 8: return variant == 1 ? ms_pick_dv<8, kMsWarpsBig, 1, false>(pv, fast) : (variant == 2 ? ms_pick_dv<8, kMsWarps, 2, false>(pv, fast) : ms_pick_dv<8, kMsWarps, 1, false>(pv, fast));
+    case 16: return ms_pick_dv<16, kMsWarps, 1, false>(pv, fast);
+    case 24: return ms_pick_dv<24, kMsWarps, 1, false>(pv, fast);
+    case 32: return ms_pick_dv<32, kMsWarps, 1, false>(pv, fast);
     }
     return nullptr;
 }
@@ -119,14 +130,12 @@ struct Geometry {
 }  // namespace
 
 // Extra per-plan state that needs the kernel types.
-typedef void (*ms_lane_kernel_t)(LaneTables, const uint16_t *, MsConst, DecodeIO, LaneScratch);
 struct PlanKernels {
     ms_kernel_t ms = nullptr;
     MsTables ms_tab{};
     int ms_full_regions = 0;
     int ms_team = 1;           // warps per shot of the warp-per-shot min-sum kernel
-    ms_lane_kernel_t ms_lane = nullptr;
-    LaneTables lane_tab{};
+    bool ms_spec = false;      // the plan holds merged steps (SPEC kernel instance)
     bp_kernel_t bp = nullptr;
     const void *bf = nullptr;  // bit-flipping kernel of the plan (dense or sparse formulation)
     const void *ng = nullptr;  // naive-greedy kernel of the plan (tables in shared memory or through L1)
@@ -294,31 +303,69 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             }
             pk->ms_full_regions = full_regions;
             int dc_inst = 0, dv_inst = 0, dmin = 0;
-            pk->ms = ms_select(dc, dv, full_regions, 0, &dc_inst, &dv_inst, &dmin);
+            pk->ms = ms_select(dc, dv, full_regions, 0, false, &dc_inst, &dv_inst, &dmin);
             if (!pk->ms) return bail(QLDPC_ETOOBIG, "min-sum kernels are instantiated for row weight <= 32 and column weight <= 16");
-            MsGraphView gv{m, n, E, p->row_ptr.data(), p->col_idx.data(), p->col_ptr.data(), p->row_idx.data(), nl, p->layer_ptr.data(), p->layer_chk.data()};
-            MsPlanLayout pl;
-            ms_plan_layout(gv, dc_inst, dv_inst, dmin, /*search=*/true, pl);
+            // ---- merged steps: runs of consecutive layers with pairwise disjoint variable sets (the single-check layers of the
+            // serial schedule inside a circulant block row) become one step of the kernel, which commits them sub-layer by
+            // sub-layer only when the convergence test could fire (ms_kernel.cuh).  Layer 0 stays alone (its first pass uses the
+            // binary32-rounded prior); a run holds at most 32 layers and `max_vars` variables (one quad trip per warp).
+            auto group_layers = [&](int max_vars, std::vector<int> &grp) {
+                grp.assign(1, 0);
+                std::vector<int> mark(n, -1);
+                int gid = 0, cur_vars = 0, cur_sub = 0;
+                for (int l = 0; l < nl; ++l) {
+                    const std::vector<int> vs = layer_vars(l);
+                    bool ok = l > 1 && cur_sub < 32 && cur_vars + (int)vs.size() <= max_vars;
+                    for (size_t x = 0; ok && x < vs.size(); ++x) ok = mark[vs[x]] != gid;
+                    if (!ok && l > 0) { grp.push_back(l); ++gid; cur_vars = 0; cur_sub = 0; }
+                    for (int v : vs) mark[v] = gid;
+                    cur_vars += (int)vs.size();
+                    ++cur_sub;
+                }
+                grp.push_back(nl);
+            };
+            auto max_group_checks = [&](const std::vector<int> &grp) {
+                int mx = 0;
+                for (size_t g2 = 0; g2 + 1 < grp.size(); ++g2) mx = std::max(mx, p->layer_ptr[grp[g2 + 1]] - p->layer_ptr[grp[g2]]);
+                return mx;
+            };
+            static const bool merge_env = [] { const char *ev = getenv("QLDPC_MS_MERGE"); return !ev || atoi(ev) != 0; }();   // tuning knob
+            const bool can_merge = merge_env && ms_spec_available(dc_inst) && o->reserved != 1;
+            std::vector<int> grp;                       // step -> first layer
             // Teams of two warps per shot: when the shot state allows only few shots per SM (LP118_2, Tanner: 10), one warp per
             // shot leaves the schedulers idle.  Decided on the state size (tables are ~10-35 KB), row-weight class 8 only.
+            int W = 1;
             {
+                MsPlanLayout probe_pl;
+                ms_plan_layout(MsGraphView{m, n, E, p->row_ptr.data(), p->col_idx.data(), p->col_ptr.data(), p->row_idx.data(), 0, p->layer_ptr.data(), p->layer_chk.data()},
+                               dc_inst, dv_inst, dmin, /*search=*/false, probe_pl);
                 MsTables probe{};
-                probe.n = n; probe.mw = t.mw; probe.c2v_words = pl.c2v_words;
+                probe.n = n; probe.mw = t.mw; probe.c2v_words = probe_pl.c2v_words;
                 const size_t st = ms_layout(probe).bytes;
-                int max_layer2 = 0;
-                for (int l = 0; l < nl; ++l) max_layer2 = std::max(max_layer2, p->layer_ptr[l + 1] - p->layer_ptr[l]);
-                int W = (dc_inst == 8 && st * 13 > (size_t)kMaxSmemPerCta - 24 * 1024 && max_layer2 >= 16) ? 2 : 1;
+                if (can_merge) group_layers(256, grp);
+                else { grp.resize(nl + 1); for (int l = 0; l <= nl; ++l) grp[l] = l; }
+                W = (dc_inst == 8 && st * 13 > (size_t)kMaxSmemPerCta - 24 * 1024 && max_group_checks(grp) >= 16) ? 2 : 1;
                 if (const char *ev = getenv("QLDPC_MS_TEAM")) { const int w2 = atoi(ev); if (w2 == 1 || (w2 == 2 && dc_inst == 8)) W = w2; }   // tuning knob
-                pk->ms_team = W;
-                if (W == 2) {
-                    pl = MsPlanLayout();
-                    ms_plan_layout(gv, dc_inst, dv_inst, dmin, /*search=*/true, pl, 2);
-                    int a1, a2, a3;
-                    pk->ms = ms_select(dc, dv, full_regions, 2, &a1, &a2, &a3);
-                }
+                if (W == 1 && can_merge) group_layers(128, grp);
             }
+            pk->ms_team = W;
+            // merging pays when it removes most of the steps (serial schedules: 450 -> 16); a layered schedule whose cross-wired
+            // partition happens to hold a few disjoint neighbours keeps its layers (and the 32-warp instances)
+            if ((int)grp.size() - 1 < nl && 2 * ((int)grp.size() - 1) > nl) { grp.resize(nl + 1); for (int l = 0; l <= nl; ++l) grp[l] = l; }
+            const int nsteps = (int)grp.size() - 1;
+            const bool spec = nsteps < nl;
+            std::vector<int> step_ptr(nsteps + 1);       // step -> range in layer_chk
+            for (int g2 = 0; g2 <= nsteps; ++g2) step_ptr[g2] = p->layer_ptr[grp[g2]];
+            pk->ms_spec = spec;
+            if (spec || W == 2) {
+                int a1, a2, a3;
+                pk->ms = ms_select(dc, dv, full_regions, W == 2 ? 2 : 0, spec, &a1, &a2, &a3);
+            }
+            MsGraphView gv{m, n, E, p->row_ptr.data(), p->col_idx.data(), p->col_ptr.data(), p->row_idx.data(), nsteps, step_ptr.data(), p->layer_chk.data()};
+            MsPlanLayout pl;
+            ms_plan_layout(gv, dc_inst, dv_inst, dmin, /*search=*/true, pl, W);
             p->plan_wavefronts = pl.wavefronts; p->plan_wavefronts_ideal = pl.ideal;
-            mt.m = m; mt.n = n; mt.E = E; mt.dc = dc_inst; mt.dv = dv; mt.nl = nl; mt.mw = t.mw; mt.nw = t.nw;
+            mt.m = m; mt.n = n; mt.E = E; mt.dc = dc_inst; mt.dv = dv; mt.nl = nsteps; mt.mw = t.mw; mt.nw = t.nw;
             mt.n_pad = (n + 63) & ~63;
             for (int x = 0; x < kMsMaxDv; ++x) { mt.cnt4[x] = 4 * pl.cnt[x]; mt.coff4[x] = 4 * pl.coff[x]; }
             mt.c2v_words = pl.c2v_words;
@@ -342,19 +389,36 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
                 }
             if (pl.lvar.size() > 65535) return bail(QLDPC_ETOOBIG, "per-layer variable lists exceed 65535 entries");
             b.resize((b.size() + 7) & ~size_t(7), 0);              // 16-byte aligned records
-            mt.off_layer = put(8 * nl);
-            for (int l = 0; l < nl; ++l) {
+            mt.off_layer = put(8 * nsteps);
+            for (int l = 0; l < nsteps; ++l) {
                 uint16_t *r = &b[mt.off_layer + 8 * l];
-                r[0] = (uint16_t)p->layer_ptr[l]; r[1] = (uint16_t)p->layer_ptr[l + 1]; r[2] = (uint16_t)pl.lpc[l];
+                r[0] = (uint16_t)step_ptr[l]; r[1] = (uint16_t)step_ptr[l + 1]; r[2] = (uint16_t)pl.lpc[l];
                 r[3] = (uint16_t)pl.lvar_ptr[l]; r[4] = (uint16_t)pl.lvar_ptr[l + 1];
                 bool single = pl.lvar_ptr[l + 1] > pl.lvar_ptr[l];
                 for (int x = pl.lvar_ptr[l + 1] - 32; single && x < pl.lvar_ptr[l + 1]; ++x) single = (pl.lvar[x] >> 16) == 4u * (uint32_t)n;
                 r[5] = single ? 1 : 0;
+                r[6] = (uint16_t)(grp[l + 1] - grp[l] > 1 ? grp[l + 1] - grp[l] : 0);
+                if (r[6] && pl.lvar_ptr[l + 1] - pl.lvar_ptr[l] > 64 * W) return bail(QLDPC_EINVAL, "internal: merged step exceeds one quad trip per warp");
             }
             mt.off_layer_chk = put((int)p->layer_chk.size());
             for (size_t x = 0; x < p->layer_chk.size(); ++x) b[mt.off_layer_chk + x] = (uint16_t)p->layer_chk[x];
             mt.off_lvar = put32((int)pl.lvar.size());
             for (size_t x = 0; x < pl.lvar.size(); ++x) set32(mt.off_lvar, (int)x, pl.lvar[x]);
+            // sub-layer (within its merged step) of every listed variable; a variable belongs to one layer of a run
+            mt.off_lsub = put(spec ? (int)pl.lvar.size() : 0);
+            if (spec) {
+                std::vector<int> vsub(n + 1, 0);
+                for (int l = 0; l < nsteps; ++l) {
+                    for (int ll = grp[l]; ll < grp[l + 1]; ++ll)
+                        for (int q = p->layer_ptr[ll]; q < p->layer_ptr[ll + 1]; ++q)
+                            for (int x = p->row_ptr[p->layer_chk[q]]; x < p->row_ptr[p->layer_chk[q] + 1]; ++x) vsub[p->col_idx[x]] = ll - grp[l];
+                    for (int x = pl.lvar_ptr[l]; x < pl.lvar_ptr[l + 1]; ++x) {
+                        const int ja = (int)(pl.lvar[x] & 0xffffu) / 4, jb = (int)(pl.lvar[x] >> 16) / 4;
+                        const int sa = ja < n ? vsub[pl.order[ja]] : 0, sb2 = jb < n ? vsub[pl.order[jb]] : 0;
+                        b[mt.off_lsub + x] = (uint16_t)(sa | (sb2 << 8));
+                    }
+                }
+            }
             // CSC in the renumbering (flip handling)
             mt.off_col_ptr = put(n + 2);
             mt.off_col_chk = put(E);
@@ -479,9 +543,9 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             return bail(QLDPC_ETOOBIG, "decoder state of one shot does not fit in 227 KB of shared memory");
         const int warps_fit = (int)std::min<size_t>(64, ((size_t)kMaxSmemPerCta - blob_bytes) / state);
         int warps = std::min(warps_fit, is_ms ? kMsWarps : 32);
-        if (is_ms && pk->ms_team == 1 && warps_fit > kMsWarps && pk->ms_tab.dc <= 8) {           // small shot state: the 32-warp instance
+        if (is_ms && pk->ms_team == 1 && !pk->ms_spec && warps_fit > kMsWarps && pk->ms_tab.dc <= 8) {           // small shot state: the 32-warp instance
             int a1, a2, a3;
-            pk->ms = ms_select(dc, dv, pk->ms_full_regions, 1, &a1, &a2, &a3);
+            pk->ms = ms_select(dc, dv, pk->ms_full_regions, 1, false, &a1, &a2, &a3);
             fn = (const void *)pk->ms;
             warps = std::min(warps_fit, kMsWarpsBig);
         }
@@ -494,77 +558,6 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
         p->smem_bytes = blob_bytes + (size_t)warps * state;
         p->grid = p->sm_count;
         CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta));   // per function, shared by all plans
-
-        // ---- lane-per-shot variant for serial-like schedules (every layer a single check); opts.reserved: 0 auto, 1 warp, 2 lane
-        int max_layer = 0;
-        for (int l = 0; l < nl; ++l) max_layer = std::max(max_layer, p->layer_ptr[l + 1] - p->layer_ptr[l]);
-        const int dc_true = p->row_w;
-        const bool lane_ok = is_ms && o->prior_llr >= 0.0 && o->max_iter >= 1 && dc_true <= 32 && dv <= 16 && (long long)m * dc_true <= 65535;
-        const bool want_lane = o->reserved == 2 || (o->reserved == 0 && max_layer == 1 && dc_true <= 8);
-        if (lane_ok && want_lane) {
-            LaneTables &lt = pk->lane_tab;
-            std::vector<uint16_t> lb;
-            auto lput = [&](int count) { int off = (int)lb.size(); lb.resize(lb.size() + count, 0); return off; };
-            lt.m = m; lt.n = n; lt.dc = dc_true; lt.dv = dv; lt.nl = nl; lt.mw = t.mw; lt.nw = t.nw;
-            std::vector<int> flc(m, 0xFFFF), flv(n, 0xFFFF);
-            for (int l = nl - 1; l >= 0; --l)
-                for (int q = p->layer_ptr[l]; q < p->layer_ptr[l + 1]; ++q) flc[p->layer_chk[q]] = l;
-            for (int i = 0; i < m; ++i)
-                for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x) flv[p->col_idx[x]] = std::min(flv[p->col_idx[x]], flc[i]);
-            lt.off_chk_var = lput(m * dc_true);
-            std::fill(lb.begin() + lt.off_chk_var, lb.end(), kPad);
-            for (int i = 0; i < m; ++i)
-                for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x) lb[lt.off_chk_var + i * dc_true + (x - p->row_ptr[i])] = (uint16_t)p->col_idx[x];
-            lt.off_var_ptr = lput(n + 1);
-            for (int j = 0; j <= n; ++j) lb[lt.off_var_ptr + j] = (uint16_t)p->col_ptr[j];
-            lt.off_var_edge = lput(E); lt.off_var_chk = lput(E); lt.off_var_fl = lput(E);
-            for (int x = 0; x < E; ++x) {
-                lb[lt.off_var_edge + x] = (uint16_t)(p->row_idx[x] * dc_true + col_slot[x]);
-                lb[lt.off_var_chk + x] = (uint16_t)p->row_idx[x];
-                lb[lt.off_var_fl + x] = (uint16_t)flc[p->row_idx[x]];
-            }
-            lt.off_layer_ptr = lput(nl + 1);
-            for (int l = 0; l <= nl; ++l) lb[lt.off_layer_ptr + l] = (uint16_t)p->layer_ptr[l];
-            lt.off_layer_chk = lput((int)p->layer_chk.size());
-            for (size_t x = 0; x < p->layer_chk.size(); ++x) lb[lt.off_layer_chk + x] = (uint16_t)p->layer_chk[x];
-            // unpadded per-layer variable lists
-            std::vector<int> lp(nl + 1, 0);
-            std::vector<uint16_t> lv;
-            std::vector<char> seen2(n, 0);
-            for (int l = 0; l < nl; ++l) {
-                std::vector<int> vs;
-                for (int q = p->layer_ptr[l]; q < p->layer_ptr[l + 1]; ++q) {
-                    const int i = p->layer_chk[q];
-                    for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x)
-                        if (!seen2[p->col_idx[x]]) { seen2[p->col_idx[x]] = 1; vs.push_back(p->col_idx[x]); }
-                }
-                std::sort(vs.begin(), vs.end());
-                for (int v : vs) { seen2[v] = 0; lv.push_back((uint16_t)v); }
-                lp[l + 1] = (int)lv.size();
-            }
-            lt.off_lvar_ptr = lput(nl + 1);
-            for (int l = 0; l <= nl; ++l) lb[lt.off_lvar_ptr + l] = (uint16_t)lp[l];
-            lt.off_lvar_idx = lput((int)lv.size());
-            std::copy(lv.begin(), lv.end(), lb.begin() + lt.off_lvar_idx);
-            lt.off_fl_chk = lput(m);
-            for (int i = 0; i < m; ++i) lb[lt.off_fl_chk + i] = (uint16_t)flc[i];
-            lt.off_fl_var = lput(n);
-            for (int j = 0; j < n; ++j) lb[lt.off_fl_var + j] = (uint16_t)flv[j];
-            lb.resize((lb.size() + 7) & ~size_t(7), 0);
-            lt.len = (int)lb.size();
-            p->lane_smem = (size_t)lt.len * 2;
-            if (lv.size() <= 65535 && p->lane_smem * 2 <= (size_t)kMaxSmemPerCta) {
-                if (dc_true <= 4 && dv <= 4) pk->ms_lane = ms_lane_kernel<4, 4>;
-                else if (dc_true <= 8 && dv <= 5) pk->ms_lane = ms_lane_kernel<8, 5>;
-                else if (dc_true <= 18 && dv <= 9) pk->ms_lane = ms_lane_kernel<18, 9>;
-                else pk->ms_lane = ms_lane_kernel<32, 16>;
-                if ((rc = upload(&p->d_lane_blob, lb))) return rc;
-                CU_TRY(cudaFuncSetAttribute((const void *)pk->ms_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta));
-                p->use_lane = true;
-                p->lane_forced = o->reserved == 2;
-                p->lane_grid = p->sm_count * 2;
-            }
-        }
     } else {
         const int warps = 8;
         const bool bf_sparse = o->dec_type == QLDPC_BF && t.mw <= 32;
@@ -604,7 +597,7 @@ int qldpc_plan_destroy(qldpc_plan *p)
 {
     if (!p) return QLDPC_OK;
     cudaSetDevice(p->device);
-    cudaFree(p->d_blob); cudaFree(p->d_lane_blob); cudaFree(p->d_row_ptr); cudaFree(p->d_col_idx); cudaFree(p->d_col_ptr); cudaFree(p->d_row_idx);
+    cudaFree(p->d_blob); cudaFree(p->d_row_ptr); cudaFree(p->d_col_idx); cudaFree(p->d_col_ptr); cudaFree(p->d_row_idx);
     cudaFree(p->d_hbits); cudaFree(p->d_hcol); cudaFree(p->d_lcol); cudaFree(p->d_work); cudaFree(p->d_fail_count);
     for (int s = 0; s < 7; ++s) if (p->scratch[s]) cudaFree(p->scratch[s]);
     delete kernels_of(p);
@@ -650,11 +643,13 @@ int64_t qldpc_plan_info(const qldpc_plan *p, int what)
     case 8: return p->row_w;
     case 9: return p->tab.dv;
     case 10: return p->rank_h;
-    case 11: return p->use_lane ? 1 : 0;
+    case 11: return 0;   // reserved
     case 12: return p->plan_wavefronts;
     case 13: return p->plan_wavefronts_ideal;
     case 14: return (int64_t)p->state_bytes;
     case 15: return p->logical_k;
+    case 16: return p->opts.dec_type == QLDPC_MS ? reinterpret_cast<PlanKernels *>(p->scratch[7])->ms_tab.nl : p->tab.nl;   // steps per iteration
+    case 17: return p->opts.dec_type == QLDPC_MS ? reinterpret_cast<PlanKernels *>(p->scratch[7])->ms_team : 1;
     }
     return -1;
 }
@@ -668,7 +663,6 @@ static int launch_decode(qldpc_plan *p, const uint32_t *syn, int64_t shots, uint
     io.syn = syn; io.ehat = ehat; io.iters = iters; io.conv = conv; io.llr = llr; io.shots = shots;
     io.work_counter = p->d_work + slot;
     io.fail_count = fail_count; io.fail_shot = fail_shot; io.fail_llr = fail_llr; io.fail_cap = fail_cap;
-    io.shot_list = nullptr; io.list_len = nullptr; io.defer_count = nullptr; io.defer_list = nullptr; io.defer_iters = 0;
     CU_TRY(cudaMemsetAsync(p->d_work + slot, 0, sizeof(unsigned long long), st));
     const int grid = (int)std::min<int64_t>(p->grid, (shots + p->shots_per_cta - 1) / p->shots_per_cta);
     const qldpc_opts &o = p->opts;
@@ -682,46 +676,7 @@ static int launch_decode(qldpc_plan *p, const uint32_t *syn, int64_t shots, uint
             if ((double)f < T) f = std::nextafterf(f, INFINITY);
             c.Tf = f;
         }
-        // automatic choice: the lane kernel needs a batch that fills its grid (2 CTAs x 8 warps x 32 shots per SM).  Measured on
-        // LP118_2 serial, p = 0.05, with the hand-over of slow shots: 1.61M vs 0.88M shots/s (warp kernel) at 10^6 shots,
-        // 0.91M vs 0.74M at 10^5 shots (with OSD)
-        static const int force = [] { const char *ev = getenv("QLDPC_MS_KERNEL"); return !ev ? 0 : (ev[0] == 'w' ? 1 : (ev[0] == 'l' ? 2 : 0)); }();   // tuning knob
-        if (p->use_lane && force != 1 && (p->lane_forced || force == 2 || shots >= 65536)) {
-            PlanKernels *pk = kernels_of(p);
-            const LaneTables &lt = pk->lane_tab;
-            const int lgrid = (int)std::min<int64_t>(p->lane_grid, (shots + 255) / 256);
-            const size_t warps = (size_t)lgrid * 8;
-            const size_t b_c2v = warps * lt.m * lt.dc * 32 * 4, b_S = warps * lt.n * 32 * 4, b_par = warps * lt.mw * 64 * 4,
-                         b_eb = warps * lt.nw * 32 * 4;
-            int rc2 = ensure_scratch(p, 3, b_c2v + b_S + b_par + b_eb + 1024);
-            if (rc2) return rc2;
-            LaneScratch sc;
-            unsigned char *sb = (unsigned char *)p->scratch[3];
-            sc.c2v = (float *)sb; sc.S = (float *)(sb + b_c2v); sc.par = (uint32_t *)(sb + b_c2v + b_S);
-            sc.eb = (uint32_t *)(sb + b_c2v + b_S + b_par);
-            // shots that need more than kLaneIters iterations are deferred to the warp-per-shot kernel (second launch below)
-            static const int kLaneIters = [] { const char *ev = getenv("QLDPC_LANE_ITERS"); const int v = ev ? atoi(ev) : 0; return v > 0 ? v : 6; }();   // tuning knob
-            const bool defer = o.max_iter > kLaneIters;
-            if (defer) {
-                if ((rc2 = ensure_scratch(p, 4, (size_t)shots * sizeof(int) + 16))) return rc2;
-                io.defer_count = (int *)p->scratch[4];
-                io.defer_list = (int *)p->scratch[4] + 4;
-                io.defer_iters = kLaneIters;
-                CU_TRY(cudaMemsetAsync(io.defer_count, 0, sizeof(int), st));
-            }
-            pk->ms_lane<<<lgrid, 256, p->lane_smem, st>>>(lt, p->d_lane_blob, c, io, sc);
-            if (defer) {
-                g_launches++;
-                CU_TRY(cudaGetLastError());
-                DecodeIO io2 = io;
-                io2.shot_list = io.defer_list; io2.list_len = io.defer_count;
-                io2.defer_count = nullptr; io2.defer_list = nullptr;
-                CU_TRY(cudaMemsetAsync(p->d_work + slot, 0, sizeof(unsigned long long), st));
-                pk->ms<<<p->grid, p->threads, p->smem_bytes, st>>>(pk->ms_tab, p->d_blob, c, io2);
-            }
-        } else {
-            kernels_of(p)->ms<<<grid, p->threads, p->smem_bytes, st>>>(kernels_of(p)->ms_tab, p->d_blob, c, io);
-        }
+        kernels_of(p)->ms<<<grid, p->threads, p->smem_bytes, st>>>(kernels_of(p)->ms_tab, p->d_blob, c, io);
         break;
     }
     case QLDPC_BP: {

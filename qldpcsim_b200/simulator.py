@@ -77,7 +77,7 @@ class Pipeline:
     """Device pipeline for one (Hx, Hz, p, decoder configuration): two decode plans + sampler + classifier."""
 
     def __init__(self, Hx, Hz, p: float, decType: str = "MS", decIterations: int = 99, decSchedule: str = "F",
-                 OSDorder: int = -1, device: Optional[int] = None, logicals: bool = False):
+                 OSDorder: int = -1, device: Optional[int] = None, logicals: bool = False, kernel: str = "auto"):
         Hx = (np.asarray(Hx) % 2).astype(np.int8)
         Hz = (np.asarray(Hz) % 2).astype(np.int8)
         if Hx.shape[1] != Hz.shape[1]:
@@ -94,8 +94,8 @@ class Pipeline:
         elif decType == "BF":                                                                        # simulator.py:275-276
             self.decX, self.decZ = Decoder(Hz, "BF", max_iter=50, **kw), Decoder(Hx, "BF", max_iter=50, **kw)
         elif decType == "MS":                                                                        # simulator.py:278-279
-            self.decX = Decoder(Hz, "MS", p=p / 3, max_iter=decIterations, layers=layersX, OSDorder=OSDorder, **kw)
-            self.decZ = Decoder(Hx, "MS", p=p / 3, max_iter=decIterations, layers=layersZ, OSDorder=OSDorder, **kw)
+            self.decX = Decoder(Hz, "MS", p=p / 3, max_iter=decIterations, layers=layersX, OSDorder=OSDorder, kernel=kernel, **kw)
+            self.decZ = Decoder(Hx, "MS", p=p / 3, max_iter=decIterations, layers=layersZ, OSDorder=OSDorder, kernel=kernel, **kw)
         else:                                                                                        # simulator.py:281-282
             self.decX = Decoder(Hz, "BP", p=p / 3, max_iter=decIterations, layers=layersX, **kw)
             self.decZ = Decoder(Hx, "BP", p=p / 3, max_iter=decIterations, layers=layersZ, **kw)
@@ -135,7 +135,7 @@ class Pipeline:
         return synz, synx, errx, errz
 
     # -- one pass -----------------------------------------------------------------------------------------
-    def run(self, synz, synx, errx, errz, counters=None, keep: bool = False):
+    def run(self, synz, synx, errx, errz, counters=None, keep: bool = False, mid_event=None):
         """decode X, decode Z, classify.  Returns the int64[10] device counter tensor (accumulated into `counters`)."""
         t = self.torch
         if counters is None:
@@ -143,6 +143,8 @@ class Pipeline:
         shots = synz.shape[0]
         ex, itx, cvx, _ = self.decX.decode_packed(synz, want_converged=keep)
         ez, itz, cvz, _ = self.decZ.decode_packed(synx, want_converged=keep)
+        if mid_event is not None:
+            mid_event.record(t.cuda.current_stream(self.device))
         st = t.cuda.current_stream(self.device).cuda_stream
         _lib.check(_lib.lib().qldpc_classify(self.decX.handle, self.decZ.handle, errx.data_ptr(), errz.data_ptr(),
                                             ex.data_ptr(), ez.data_ptr(), synz.data_ptr(), synx.data_ptr(),

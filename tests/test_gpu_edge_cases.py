@@ -188,14 +188,14 @@ def test_integration_md_stub_runs(cuda_device):
     assert e.shape == g["eX_ref"].shape
 
 
-LANE_CASES = [("steane", "S", 0.1, 2000), ("LP04_0", "S", 0.05, 600), ("LP04_0", "L", 0.08, 600), ("LP118_0", "L", 0.05, 400),
-              ("LP118_0", "F", 0.05, 200), ("LP118_2", "S", 0.05, 100), ("bicycle", "L", 0.03, 300), ("T", "S", 0.03, 70)]
+POSTERIOR_CASES = [("steane", "S", 0.1, 2000), ("LP04_0", "S", 0.05, 600), ("LP04_0", "L", 0.08, 600), ("LP118_0", "L", 0.05, 400),
+                   ("LP118_0", "F", 0.05, 200), ("LP118_2", "S", 0.05, 100), ("bicycle", "L", 0.03, 300), ("T", "S", 0.03, 70)]
 
 
-@pytest.mark.parametrize("code,sched,p,shots", LANE_CASES)
-def test_ms_lane_kernel_matches_oracle(code, sched, p, shots, cuda_device):
-    """The lane-per-shot min-sum kernel (forced) on serial, layered and flooding schedules, incl. llr output and a
-    shot count that leaves lanes idle / forces refills."""
+@pytest.mark.parametrize("code,sched,p,shots", POSTERIOR_CASES)
+def test_ms_posterior_matches_oracle(code, sched, p, shots, cuda_device):
+    """Estimates, iteration counts, convergence flags and the float64 posterior (what decoders.py:179-180 hands to OSDdec) of
+    every shot on serial, layered and flooding schedules."""
     from oracle import oracle
     from qldpcsim_b200 import pcmlibrary, sampler
     from qldpcsim_b200.decoders import Decoder
@@ -205,24 +205,58 @@ def test_ms_lane_kernel_matches_oracle(code, sched, p, shots, cuda_device):
     sy_z = rec[:, :Hz.shape[0]]
     lX, _ = schedule_layers(Hx, Hz, sched)
     want = oracle.Graph(Hz).decode("MS", sy_z, p=p / 3, max_iter=20, layers=lX, want_posterior=True)
-    d = Decoder(Hz, "MS", p=p / 3, max_iter=20, layers=lX, kernel="lane")
-    assert d.info()["lane_kernel"] == 1
-    got = d.decode(sy_z, want_llr=True)
-    assert np.array_equal(got["e_hat"], want["e_hat"]) and np.array_equal(got["iters"], want["iters"])
-    assert np.array_equal(got["converged"], want["converged"])
-    assert np.array_equal(got["posterior"], want["posterior"])
-    dw = Decoder(Hz, "MS", p=p / 3, max_iter=20, layers=lX, kernel="warp")
-    assert dw.info()["lane_kernel"] == 0
-    gw = dw.decode(sy_z, want_llr=True)
-    assert np.array_equal(gw["e_hat"], want["e_hat"]) and np.array_equal(gw["posterior"], want["posterior"])
+    for kernel in ("auto", "plain"):
+        got = Decoder(Hz, "MS", p=p / 3, max_iter=20, layers=lX, kernel=kernel).decode(sy_z, want_llr=True)
+        assert np.array_equal(got["e_hat"], want["e_hat"]) and np.array_equal(got["iters"], want["iters"])
+        assert np.array_equal(got["converged"], want["converged"])
+        assert np.array_equal(got["posterior"], want["posterior"])
 
 
-def test_ms_lane_kernel_with_osd(cuda_device):
-    from conftest import load_golden
+MERGE_CASES = [("LP04_0", "S", 0.06, 3000, 50), ("LP118_0", "S", 0.06, 1500, 50), ("LP118_2", "S", 0.05, 1500, 50), ("T", "S", 0.04, 800, 50),
+               ("LP118_2", "S", 0.09, 300, 8), ("steane", "S", 0.1, 2000, 50)]
+
+
+@pytest.mark.parametrize("code,sched,p,shots,iters", MERGE_CASES)
+def test_ms_merged_steps_match_oracle(code, sched, p, shots, iters, cuda_device):
+    """Serial schedule: runs of single-check layers with disjoint variable sets are executed as one step of the kernel (SPEC
+    instances) and committed sub-layer by sub-layer only near convergence.  Estimates, iteration counts (which encode the layer
+    at which the reference's per-layer test fires, decoders.py:175-176) and the float64 posterior of EVERY shot -- converged in
+    the middle of a run or not -- must equal the oracle's and the unmerged kernel's."""
+    from oracle import oracle
+    from qldpcsim_b200 import pcmlibrary, sampler
     from qldpcsim_b200.decoders import Decoder
     from qldpcsim_b200.pcm import schedule_layers
-    g = load_golden("LP04_0_MS_L_OSD0_p10")
-    lX, _ = schedule_layers(g["Hx"], g["Hz"], "L")
-    a = Decoder(g["Hz"], "MS", p=0.1 / 3, max_iter=8, layers=lX, OSDorder=0, kernel="lane").decode(g["sy_z"])
-    b = Decoder(g["Hz"], "MS", p=0.1 / 3, max_iter=8, layers=lX, OSDorder=0, kernel="warp").decode(g["sy_z"])
-    assert np.array_equal(a["e_hat"], b["e_hat"]) and np.array_equal(a["iters"], g["itX"])
+    Hx, Hz = [(h % 2).astype(np.int8) for h in pcmlibrary.by_name(code)]
+    rec = sampler.sample_record(Hx, Hz, p, shots, seed=13)
+    for H, sy, lay in ((Hz, rec[:, :Hz.shape[0]], schedule_layers(Hx, Hz, sched)[0]),
+                       (Hx, rec[:, Hz.shape[0]:Hz.shape[0] + Hx.shape[0]], schedule_layers(Hx, Hz, sched)[1])):
+        want = oracle.Graph(H).decode("MS", sy, p=p / 3, max_iter=iters, layers=lay, want_posterior=True)
+        d = Decoder(H, "MS", p=p / 3, max_iter=iters, layers=lay, kernel="auto")
+        info = d.info()
+        if code != "steane":
+            assert info["steps_per_iteration"] * 4 < info["n_layers"], info       # merging is active
+        got = d.decode(sy, want_llr=True)
+        assert np.array_equal(got["iters"], want["iters"])
+        assert np.array_equal(got["e_hat"], want["e_hat"]) and np.array_equal(got["converged"], want["converged"])
+        assert np.array_equal(got["posterior"], want["posterior"])
+        plain = Decoder(H, "MS", p=p / 3, max_iter=iters, layers=lay, kernel="plain")
+        assert plain.info()["steps_per_iteration"] == plain.info()["n_layers"]
+        gp = plain.decode(sy, want_llr=True)
+        assert np.array_equal(gp["e_hat"], want["e_hat"]) and np.array_equal(gp["iters"], want["iters"])
+        assert np.array_equal(gp["posterior"], want["posterior"])
+
+
+def test_decode_host_many_chunks_serial(cuda_device):
+    """qldpc_decode_host keeps two chunks in flight on two streams; their scratch (work counters, staging buffers, hand-over
+    lists) must be per slot.  Serial-schedule plan, more than two chunks, against the device-resident path."""
+    import torch
+    from qldpcsim_b200 import pcmlibrary, simulator
+    Hx, Hz = pcmlibrary.by_name("LP118_2")
+    shots = 3 * (1 << 18) + 4321
+    pipe = simulator.Pipeline(Hx, Hz, 0.05, "MS", 50, "S")
+    synz, _, _, _ = pipe.sample_device(shots, 5, 0)
+    e_dev, it_dev, cv_dev, _ = pipe.decX.decode_packed(synz)
+    e_h, it_h, cv_h, _ = pipe.decX.decode_host_packed(synz.cpu().numpy().view(np.uint32))
+    torch.cuda.synchronize()
+    assert np.array_equal(e_h.view(np.int32), e_dev.cpu().numpy()) and np.array_equal(it_h, it_dev.cpu().numpy())
+    assert np.array_equal(cv_h, cv_dev.cpu().numpy())
