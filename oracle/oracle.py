@@ -29,8 +29,8 @@ DEC_TYPES = {"NG": 0, "BF": 1, "MS": 2, "BP": 3}
 
 def build(force: bool = False) -> str:
     """Compile qldpc_oracle.c with the committed Makefile (gcc only)."""
-    src = os.path.join(_HERE, "qldpc_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("qldpc_oracle.c", "npymath.h", "npymath_tables.inc")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs):
         subprocess.run(["make", "-C", _HERE, "-B", "libqldpc_oracle.so"], check=True, capture_output=True)
     return _LIB_PATH
 
@@ -51,6 +51,8 @@ def _load():
     lib.orc_osd.restype = i32
     lib.orc_osd.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.orc_osd_reliability.argtypes = [vp, i32, vp]
+    lib.orc_npy_tanh.argtypes = [vp, vp, i64]
+    lib.orc_npy_arctanh.argtypes = [vp, vp, i64]
     lib.orc_rank.restype = i32
     lib.orc_rank.argtypes = [vp, i32, i32]
     _lib = lib
@@ -181,6 +183,22 @@ class Graph:
         if rc != 0:
             raise RuntimeError(f"oracle OSD failed rc={rc}")
         return e
+
+
+def npy_tanh(x: np.ndarray) -> np.ndarray:
+    """np.tanh as NumPy 2.3.5 evaluates it for float64 (npymath.h: simd_tanh_f64 restated)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    _load().orc_npy_tanh(_ptr(x), _ptr(y), x.size)
+    return y
+
+
+def npy_arctanh(x: np.ndarray) -> np.ndarray:
+    """np.arctanh as NumPy 2.3.5 evaluates it for float64 on AVX-512 hosts (npymath.h: __svml_atanh8_ha restated)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    _load().orc_npy_arctanh(_ptr(x), _ptr(y), x.size)
+    return y
 
 
 def gf2_rank(A: np.ndarray) -> int:

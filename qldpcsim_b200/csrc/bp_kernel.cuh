@@ -14,14 +14,14 @@
 //     cooperatively and maintain the count of unsatisfied checks (decoders.py:280-285).
 #pragma once
 #include "common.cuh"
+#include "npymath.cuh"
 
 namespace qldpc {
 
-// tanh / atanh are the CUDA math library's.  A branch-free replacement (expm1-based tanh(x/2), fdlibm-style log1p for
-// 2*atanh, max error 2.3 / 1.7 ulp against 200-bit references, glibc: 1.9 / 1.5) was written and measured this round: against the
-// 1600-decode golden of the unmodified reference (tests/golden/big_LP118_0_BP_F_p05_X.npz) it agrees on exactly as many decodes
-// as this version and as the glibc oracle (99.69 %: NumPy's SIMD tanh is a third implementation, and non-converging decodes are
-// chaotic in the last bit), but with five IEEE divisions per edge it was SLOWER (2.67 vs 3.12 M shots/s), so it was dropped.
+// tanh / atanh are NumPy's own routines (npymath.cuh): with them the kernel is bit-identical to the reference on all 4800 decodes
+// of the three large reference goldens (tests/golden/big_LP118_0_BP_F_p{02,05,10}_X.npz).  With the CUDA math library's
+// functions (round 1) the agreement was 99.69 % at p = 0.05 -- NumPy's SIMD tanh differs from any libm in the last bit on a
+// quarter of all arguments.
 struct BpConst {
     double L0;     // prior LLR (decoders.py:232)
     double eps;    // decoders.py:195
@@ -35,6 +35,9 @@ struct BpSmemLayout {
     int off_team;  // 16 bytes: shot index mailbox (int64), unsatisfied-check count (int32)
     int bytes;
 };
+
+// graph tables + the NumPy math tables, in front of the per-team state
+__host__ __device__ inline int bp_table_bytes(const Tables &t) { return ((t.len * 2 + 15) & ~15) + (int)((sizeof(NpymTables) + 15) & ~size_t(15)); }
 
 __host__ __device__ inline BpSmemLayout bp_layout(const Tables &t)
 {
@@ -95,7 +98,10 @@ __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
         for (int i = threadIdx.x; i < t.len / 8; i += blockDim.x) dst[i] = src[i];
     }
+    NpymTables *npym_tab = reinterpret_cast<NpymTables *>(smem + ((t.len * 2 + 15) & ~15));
+    npym_stage_tables(npym_tab);
     __syncthreads();
+    const NpymTables &nt = *npym_tab;
     const uint16_t *var_tab = tab + t.off_var;          // byte offsets 4*j
     const uint16_t *col_ptr = tab + t.off_col_ptr;
     const uint16_t *col_pos = tab + t.off_col_pos;
@@ -113,7 +119,7 @@ __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint
     const int team = warp / W, sub = warp % W;
     const int tl = sub * 32 + lane;                            // thread index within the team
     constexpr int TT = 32 * W;                                 // threads per team
-    unsigned char *base = smem + ((t.len * 2 + 15) & ~15) + (size_t)team * lay.bytes;
+    unsigned char *base = smem + bp_table_bytes(t) + (size_t)team * lay.bytes;
     double *c2v = reinterpret_cast<double *>(base + lay.off_c2v);
     double *T = reinterpret_cast<double *>(base + lay.off_T);
     uint32_t *par = reinterpret_cast<uint32_t *>(base + lay.off_par);
@@ -165,7 +171,7 @@ __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint
                     const uint32_t joff = var_tab[pos];
                     const bool valid = act && k < dc && joff != kPad;
                     double tk = 1.0;
-                    if (valid) tk = tanh(__dsub_rn(T[joff >> 2], c2v[pos]) / 2.0);     // tanh(v2c/2) (:254, :256)
+                    if (valid) tk = npym_tanh(__dsub_rn(T[joff >> 2], c2v[pos]) / 2.0, nt);     // np.tanh(v2c/2) (:254, :256)
                     double prod = 1.0;
                     for (int x = 0; x < dc; ++x)                                       // np.prod: sequential (:253-254)
                         prod = __dmul_rn(prod, __shfl_sync(full, tk, grp + x));
@@ -175,7 +181,7 @@ __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint
                             const double sg = (th2 > 0.0) ? 1.0 : ((th2 < 0.0) ? -1.0 : 0.0);
                             th2 = __dsub_rn(th2, __dmul_rn(c.eps, sg));
                         }
-                        double val = 2.0 * atanh(th2);                                 // :259
+                        double val = 2.0 * npym_arctanh(th2, nt);                      // np.arctanh (:259)
                         if ((syn[i >> 5] >> (i & 31)) & 1u) val = -val;                // :260-261
                         c2v[pos] = val;                                                // :262
                     }

@@ -505,7 +505,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             // warps is what counts, not the number of resident shots
             auto pick_team = [&](int *W_out) -> int {     // returns the number of resident warps
                 const size_t st = bp_layout(t).bytes;
-                const size_t bb = ((size_t)t.len * 2 + 15) & ~size_t(15);
+                const size_t bb = (size_t)bp_table_bytes(t);
                 const int teams_fit = (int)std::min<size_t>(32, bb + st <= (size_t)kMaxSmemPerCta ? ((size_t)kMaxSmemPerCta - bb) / st : 0);
                 int W = 1, best_warps = std::min(teams_fit, 32);
                 for (int w2 = 2; w2 <= 4 && w2 <= passes; ++w2) {
@@ -537,7 +537,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             fn = (const void *)pk->bp;
         }
         if ((rc = upload(&p->d_blob, b))) return rc;
-        const size_t blob_bytes = is_ms ? (size_t)ms_table_bytes(pk->ms_tab) : (((size_t)t.len * 2 + 15) & ~size_t(15));
+        const size_t blob_bytes = is_ms ? (size_t)ms_table_bytes(pk->ms_tab) : (size_t)bp_table_bytes(t);
         if (!fn) return bail(QLDPC_ETOOBIG, "row weight not supported");
         if (blob_bytes + state > (size_t)kMaxSmemPerCta)
             return bail(QLDPC_ETOOBIG, "decoder state of one shot does not fit in 227 KB of shared memory");

@@ -18,7 +18,7 @@ def pytest_configure(config):
 
 def golden_names():
     return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not f.endswith("codes.npz") and not os.path.basename(f).startswith("big_"))
+                  if not f.endswith("codes.npz") and not os.path.basename(f).startswith(("big_", "numpy_", "cli_")))
 
 
 def load_golden(name):

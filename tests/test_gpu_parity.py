@@ -4,7 +4,7 @@ GPU parity tests (run on the B200 box): the CUDA decoders, called through the C 
   (2) the CPU oracle on larger seeded batches;
   (3) size-independent properties at benchmark scale.
 Bars (BASELINE.json north_star): NG / BF / OSD / outcome counters bit-exact; MS hard decisions and iteration
-counts equal on >= 99.99 % of shots; BP on >= 99.9 % of shots.
+counts equal on >= 99.99 % of shots; BP on >= 99.9 % of shots.  What is asserted is stronger: MS and BP bit-exact too.
 """
 import numpy as np
 import pytest
@@ -52,9 +52,8 @@ def test_golden_decoders(name, cuda_device):
         # the arithmetic is specified to the bit, so on these small sets every shot must agree
         assert fx == 1.0 and fz == 1.0, f"{name}: MS mismatch X {np.nonzero(~sx)[0][:5]} Z {np.nonzero(~sz)[0][:5]}"
     else:
-        n = len(sx)
-        allowed = max(1, int(np.floor((1 - BP_BAR) * n)))       # sets are small: allow one shot
-        assert (~sx).sum() <= allowed and (~sz).sum() <= allowed, f"{name}: BP match {fx}, {fz}"
+        # np.tanh / np.arctanh are evaluated with NumPy's own algorithms: bit-exact like the other decoders
+        assert fx == 1.0 and fz == 1.0, f"{name}: BP mismatch X {np.nonzero(~sx)[0][:5]} Z {np.nonzero(~sz)[0][:5]}"
 
 
 @pytest.mark.parametrize("name", [n for n in golden_names() if "OSD" in n])
@@ -195,11 +194,9 @@ def test_against_oracle(code, decType, sched, p, shots, iters, cuda_device):
             assert got[k] == want[k], k
     else:
         assert sameX.mean() >= BP_BAR and sameZ.mean() >= BP_BAR, (sameX.mean(), sameZ.mean())
-        # qBLER inside the 95 % binomial interval of the oracle's
-        q_ref = 1 - want["decSuccessExact"] / shots
-        q = 1 - got["decSuccessExact"] / shots
-        half = 1.96 * np.sqrt(max(q_ref * (1 - q_ref), 1e-12) / shots) + 1.0 / shots
-        assert abs(q - q_ref) <= half
+        assert sameX.all() and sameZ.all(), "BP uses NumPy's tanh / arctanh algorithms on both sides: any mismatch is a bug"
+        for k in ("DecFailures_X", "DecFailures_Z", "decSuccessExact", "decSuccessDegen"):
+            assert got[k] == want[k], k
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -439,14 +436,16 @@ def test_outcome_classes(code, decType, sched, p, shots, cuda_device):
     assert sum(want.values()) == shots
 
 
-def test_bp_big_reference_golden(cuda_device):
-    """GPU sum-product decoder against 1600 decodes of the unmodified reference (see tests/golden/make_bp_golden.py and the
-    CPU twin of this test in test_oracle_golden.py for why the bar on this configuration is 99.5 % and not 99.9 %)."""
+@pytest.mark.parametrize("tag", ["02", "05", "10"])
+def test_bp_big_reference_goldens_bit_exact(tag, cuda_device):
+    """GPU sum-product decoder against 1600 decodes of the unmodified reference per depolarizing probability (BASELINE config
+    2's code, decoder and iteration count; p = 0.02 / 0.05 / 0.10).  The kernel evaluates np.tanh / np.arctanh with NumPy's
+    own algorithms (csrc/npymath.cuh), so every decode -- converged or not -- must be bit-identical."""
     import os
     from conftest import GOLDEN_DIR
     from qldpcsim_b200 import bitpack, pcm, pcmlibrary
     from qldpcsim_b200.decoders import Decoder
-    g = np.load(os.path.join(GOLDEN_DIR, "big_LP118_0_BP_F_p05_X.npz"))
+    g = np.load(os.path.join(GOLDEN_DIR, f"big_LP118_0_BP_F_p{tag}_X.npz"))
     Hx, Hz = [(h % 2).astype(np.int8) for h in pcmlibrary.by_name("LP118_0")]
     m, n = Hz.shape
     syn = bitpack.unpack_rows(g["syn"], m).astype(np.uint8)
@@ -454,9 +453,4 @@ def test_bp_big_reference_golden(cuda_device):
     lX, _ = pcm.schedule_layers(Hx, Hz, "F")
     out = Decoder(Hz, "BP", p=float(g["p"]) / 3, max_iter=iters, layers=lX).decode(syn)
     same = (out["e_hat"] == e_ref).all(1) & (out["iters"] == it_ref)
-    assert same.mean() >= 0.995, same.mean()
-    assert same[it_ref <= 20].all()
-    shots = len(it_ref)
-    f_ref = float(((e_ref.astype(np.int64) @ Hz.T.astype(np.int64)) % 2 != syn).any(1).mean())
-    f_gpu = float(((out["e_hat"].astype(np.int64) @ Hz.T.astype(np.int64)) % 2 != syn).any(1).mean())
-    assert abs(f_gpu - f_ref) <= 1.96 * np.sqrt(f_ref * (1 - f_ref) / shots) + 1.0 / shots
+    assert same.all(), f"p=0.{tag}: {int((~same).sum())} of {len(same)} decodes differ from the reference"

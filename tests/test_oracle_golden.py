@@ -34,11 +34,8 @@ def test_oracle_matches_reference_golden(name):
             extra = dict(OSDorder=osd, osd_perm=perm, want_posterior=True)
         o = _run(g, H, sy, lay, **extra)
         same = (o["e_hat"] == e_ref).all(axis=1) & (o["iters"] == it_ref)
-        if g["decType"] == "BP":
-            # libm tanh/atanh vs NumPy's SIMD kernels: >= 99.9 % of shots (BASELINE north_star); sets are small
-            assert (~same).sum() <= max(1, int(0.001 * len(same))), f"{name}: {same.mean()}"
-        else:
-            assert same.all(), f"{name}: oracle differs from the reference on shots {np.nonzero(~same)[0][:8]}"
+        # every decoder bit-exact, sum-product included (np.tanh / np.arctanh restated in oracle/npymath.h)
+        assert same.all(), f"{name}: oracle differs from the reference on shots {np.nonzero(~same)[0][:8]}"
         if osd >= 0:
             sel = np.nonzero(g["osd_which"] == which)[0]
             assert np.array_equal(o["posterior"][g["osd_shot"][sel]], g["osd_llr"][sel]), "posterior must be bit-identical"
@@ -89,16 +86,16 @@ def test_survey_golden_table():
         assert tuple(load_golden(name)["counters"]) == c, name
 
 
-def test_bp_big_reference_golden_documents_the_reachable_bar():
-    """1600 LP118_0 BP decodes of the unmodified reference (tests/golden/make_bp_golden.py).  The oracle uses glibc's tanh /
-    atanh, the reference NumPy's SIMD routines: decodes that converge agree to the bit, decodes that never converge are
-    chaotic in the last bit of those functions.  Measured: 99.69 % overall -- the north star's 99.9 % is not reachable on
-    this configuration without NumPy's own tanh; what is asserted is >= 99.5 %, every quickly converging decode identical,
-    and a failure rate inside the reference's 95 % binomial interval."""
+@pytest.mark.parametrize("tag", ["02", "05", "10"])
+def test_bp_big_reference_goldens_bit_exact(tag):
+    """1600 LP118_0 BP-F decodes of the unmodified reference per depolarizing probability (the ends and the middle of BASELINE
+    config 2's sweep; tests/golden/make_bp_golden.py).  With NumPy's own tanh / arctanh restated (oracle/npymath.h) the oracle
+    is bit-identical on every one of them -- including the 964 decodes at p = 0.10 that never converge.  (With glibc's
+    functions, round 1, the match was 99.69 % at p = 0.05 and 99.81 % at p = 0.10.)"""
     import os
     from conftest import GOLDEN_DIR
     from qldpcsim_b200 import bitpack, pcm, pcmlibrary
-    g = np.load(os.path.join(GOLDEN_DIR, "big_LP118_0_BP_F_p05_X.npz"))
+    g = np.load(os.path.join(GOLDEN_DIR, f"big_LP118_0_BP_F_p{tag}_X.npz"))
     Hx, Hz = [(h % 2).astype(np.int8) for h in pcmlibrary.by_name("LP118_0")]
     m, n = Hz.shape
     syn = bitpack.unpack_rows(g["syn"], m).astype(np.uint8)
@@ -106,9 +103,4 @@ def test_bp_big_reference_golden_documents_the_reachable_bar():
     lX, _ = pcm.schedule_layers(Hx, Hz, "F")
     o = oracle.Graph(Hz).decode("BP", syn, p=float(g["p"]) / 3, max_iter=iters, layers=lX)
     same = (o["e_hat"] == e_ref).all(1) & (o["iters"] == it_ref)
-    assert same.mean() >= 0.995
-    assert same[it_ref <= 20].all()
-    shots = len(it_ref)
-    f_ref = float(((e_ref.astype(np.int64) @ Hz.T.astype(np.int64)) % 2 != syn).any(1).mean())
-    f_orc = float(((o["e_hat"].astype(np.int64) @ Hz.T.astype(np.int64)) % 2 != syn).any(1).mean())
-    assert abs(f_orc - f_ref) <= 1.96 * np.sqrt(f_ref * (1 - f_ref) / shots) + 1.0 / shots
+    assert same.all(), f"p=0.{tag}: {int((~same).sum())} of {len(same)} decodes differ from the reference"

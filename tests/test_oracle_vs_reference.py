@@ -84,7 +84,10 @@ def test_live_random_irregular(seed):
     for s in range(syn.shape[0]):
         er, ir = dec.MS_decoder(H, syn[s].astype(int), p=p, max_iter=it, layers=layers, beta=beta)
         assert np.array_equal(np.asarray(er).astype(np.uint8), o["e_hat"][s]) and ir == o["iters"][s], (seed, s)
-    # BP is not compared here: on tiny irregular graphs a degree-1 variable on an unsatisfied check gets the posterior
-    # L - 2*atanh(tanh(L/2)), i.e. 0 up to the last-bit difference between NumPy's SIMD tanh/arctanh and libm, and the sign
-    # of that residual decides the bit (observed: seed 6).  BP parity is statistical (>= 99.9 % of shots, test_live /
-    # goldens on the real codes), min-sum parity is to the bit.
+    # sum-product on the same matrices: with NumPy's own tanh / arctanh restated in the oracle even the touchy cases agree
+    # (a degree-1 variable on an unsatisfied check gets the posterior L - 2*atanh(tanh(L/2)), whose sign is decided by the
+    # last bit of both functions; with libm this comparison failed on seed 6)
+    ob = oracle.Graph(H).decode("BP", syn, p=p, max_iter=it, layers=layers)
+    for s in range(syn.shape[0]):
+        er, ir = dec.BP_decoder(H, syn[s].astype(int), p=p, max_iter=it, layers=layers)
+        assert np.array_equal(np.asarray(er).astype(np.uint8), ob["e_hat"][s]) and ir == ob["iters"][s], ("BP", seed, s)
