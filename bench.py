@@ -19,9 +19,11 @@ an all-reduce of the int64[10] counters.  Prints ONE JSON line on rank 0.
               layered schedule, SURVEY.md section 8d, + bit-packed I/O) / its CUDA-event time, against the measured HBM copy
               bandwidth of MEASURED_PEAKS.json.  The kernel keeps its state in shared memory, so real DRAM traffic is
               far below the algorithmic figure; `traffic` comes from profiles/ when an ncu capture exists.
-  cpu_baseline / --impl reference : the CPU oracle (C port of the reference's decoders, OpenMP over shots) on a bounded
-              sample of the same workload on this box's host cores.  The reference itself is Python and cannot travel;
-              DESIGN.md records its own speed measured in the build container.
+  cpu_baseline / --impl reference : the reference's own CPU implementation of the path on this box's host cores, on a bounded
+              sample of the same workload: the UNMODIFIED reference (decoders.MS_decoder called as simulator.py:278-279 does,
+              pip-installed into baseline/_ref by baseline/install_reference.sh; one process per core) -- kind "reference" --
+              and, beside it, the oracle's C port of the same decoder (OpenMP over shots) -- "port".  Without baseline/_ref
+              only the port is timed.
 """
 from __future__ import annotations
 
@@ -45,8 +47,9 @@ DEC_ITERS = 50
 SCHEDULE = "L"
 SHOTS_PER_STEP = 1_000_000
 BYTES_PER_EDGE_ITER = 16.0          # layered / serial: c2v read+write, posterior read+write
-CPU_SAMPLE_SHOTS = 262144         # cpu_baseline leg: ~3.5 s wall on 16 host threads (~1 core-minute)
-REF_STEP_SHOTS = 65536            # --impl reference: ~0.9 s per step on 16 host threads
+CPU_SAMPLE_SHOTS = 262144         # cpu_baseline leg, C port: ~3.5 s wall on 16 host threads (~1 core-minute)
+REF_STEP_SHOTS = 65536            # --impl reference without baseline/_ref (C port): ~0.9 s per step on 16 host threads
+REF_PY_SHOTS_PER_CORE = 8         # unmodified reference: ~70 ms per X+Z shot and core => ~0.6 s per step
 METRIC = "shots/sec decoded (X+Z), LP118_0 MS-layered 50 it"
 UNIT = "shots/s"
 
@@ -138,6 +141,69 @@ def cpu_decode_rate(shots, seed, threads, repeat=1):
     return times
 
 
+# ---- the unmodified reference (baseline/_ref), one process per core ------------------------------------------------
+_REF = {}
+
+
+def _ref_init():
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    import warnings
+    warnings.filterwarnings("ignore")
+    from oracle import ref_loader
+    from qldpcsim_b200 import pcmlibrary
+    _REF["dec"] = ref_loader.load("decoders")
+    layerize = ref_loader.load_layerize()
+    Hx, Hz = [(h % 2).astype(np.int8) for h in pcmlibrary.by_name(CODE)]          # what simulator.load_matrix returns (:35)
+    _REF["Hx"], _REF["Hz"] = Hx, Hz
+    _REF["lX"], _REF["lZ"] = layerize(Hx, serial=False), layerize(Hz, serial=False)   # simulator.py:230-234, schedule 'L'
+
+
+def _ref_chunk(job):
+    sy_z, sy_x = job
+    dec, it = _REF["dec"], 0
+    for a, b in zip(sy_z, sy_x):
+        _, i1 = dec.MS_decoder(_REF["Hz"], a.astype(int), p=P_DEPOL / 3, max_iter=DEC_ITERS, layers=_REF["lX"], OSDorder=-1)   # :278
+        _, i2 = dec.MS_decoder(_REF["Hx"], b.astype(int), p=P_DEPOL / 3, max_iter=DEC_ITERS, layers=_REF["lZ"], OSDorder=-1)   # :279
+        it += i1 + i2
+    return it
+
+
+def reference_available():
+    from oracle import ref_loader
+    return ref_loader.available()
+
+
+class ReferencePool:
+    """Times the unmodified reference's MS decoder on `shots` shots per call, spread over `procs` worker processes."""
+
+    def __init__(self, procs):
+        import multiprocessing as mp
+        self.procs = procs
+        self.pool = mp.get_context("fork").Pool(procs, initializer=_ref_init)
+        self.pool.map(_ref_chunk, [(np.zeros((0, 1)), np.zeros((0, 1)))] * procs)          # workers up, reference imported
+
+    def rate(self, shots, seed):
+        from oracle import oracle
+        from qldpcsim_b200 import pcmlibrary, sampler
+        Hx, Hz = [(h % 2).astype(np.int8) for h in pcmlibrary.by_name(CODE)]
+        rec = sampler.sample_record(Hx, Hz, P_DEPOL, shots, seed=seed)
+        sy_z, sy_x, _, _ = oracle.split_record(rec, Hz.shape[0], Hx.shape[0], Hx.shape[1])
+        jobs = [(sy_z[a:a + 2], sy_x[a:a + 2]) for a in range(0, shots, 2)]      # small jobs: a non-converging shot costs 20x a typical one
+        t0 = time.perf_counter()
+        self.pool.map(_ref_chunk, jobs, chunksize=1)
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.pool.terminate()
+
+
+def config_block(shots):
+    """The keys both arms print (same workload, same labels)."""
+    return {"workload": workload_name(shots), "decType": "MS", "decSchedule": "L", "decIterations": DEC_ITERS, "p": P_DEPOL,
+            "shots_per_step_per_gpu": shots}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -145,17 +211,28 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     from oracle import oracle
     oracle.build()
-    times = cpu_decode_rate(REF_STEP_SHOTS, 1234, cores, repeat=args.warmup + args.steps)[args.warmup:]
+    if reference_available():
+        step_shots = max(200, REF_PY_SHOTS_PER_CORE * cores)
+        pool = ReferencePool(cores)
+        times = [pool.rate(step_shots, 1234 + k) for k in range(args.warmup + args.steps)][args.warmup:]
+        pool.close()
+        kind = "reference"
+        sample = (f"{step_shots} shots of that workload per step x {len(times)} steps, the unmodified reference (baseline/_ref, "
+                  f"decoders.MS_decoder called as simulator.py:278-279), {cores} worker processes")
+    else:
+        step_shots = REF_STEP_SHOTS
+        times = cpu_decode_rate(step_shots, 1234, cores, repeat=args.warmup + args.steps)[args.warmup:]
+        kind = "port"
+        sample = (f"{step_shots} shots per step x {len(times)} steps, oracle/qldpc_oracle.c (C port of decoders.py MS_decoder, OpenMP "
+                  f"over shots); baseline/_ref is absent")
     total = sum(times)
-    value = REF_STEP_SHOTS * len(times) / total
+    value = step_shots * len(times) / total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(SHOTS_PER_STEP), "reference_step": f"{REF_STEP_SHOTS} shots of that workload per step"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{REF_STEP_SHOTS} shots per step x {len(times)} steps, oracle/qldpc_oracle.c (C port of decoders.py "
-                                   f"MS_decoder, OpenMP over shots); the Python reference itself cannot travel to this box"},
+        "config": {**config_block(SHOTS_PER_STEP), "sample_shots_per_step": step_shots},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -289,8 +366,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(shots), "decType": "MS", "decSchedule": "L", "decIterations": DEC_ITERS, "p": P_DEPOL,
-                       "shots_per_step_per_gpu": shots, "sharding": f"shots x {world} ranks, counters all-reduced (NCCL)" if world > 1 else "single GPU",
+            "config": {**config_block(shots), "sharding": f"shots x {world} ranks, counters all-reduced (NCCL)" if world > 1 else "single GPU",
                        "l2": "inputs+outputs per step (~345 MB) exceed the 126 MB L2; 4 resident batches cycled",
                        "avg_iters_X": itX / shots, "avg_iters_Z": itZ / shots,
                        "edge_iterations_per_s": (itX + itZ) * E * world / (elapsed_ms / args.steps * 1e-3)},
@@ -312,9 +388,20 @@ def run_gpu(args):
             oracle.build()
             cores = os.cpu_count() or 1
             tcpu = cpu_decode_rate(CPU_SAMPLE_SHOTS, 1234, cores)[0]
-            line["cpu_baseline"] = {"value": CPU_SAMPLE_SHOTS / tcpu, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{CPU_SAMPLE_SHOTS} shots of the same workload (host sampler seed 1234), "
-                                              f"oracle/qldpc_oracle.c MS decode X+Z, OpenMP {cores} threads"}
+            port = {"value": CPU_SAMPLE_SHOTS / tcpu, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"{CPU_SAMPLE_SHOTS} shots of the same workload (host sampler seed 1234), "
+                              f"oracle/qldpc_oracle.c MS decode X+Z, OpenMP {cores} threads"}
+            if reference_available():
+                n_ref = max(256, 16 * cores)                    # ~70 ms per shot and core => ~1-2 s wall
+                pool = ReferencePool(cores)
+                tref = pool.rate(n_ref, 1234)
+                pool.close()
+                line["cpu_baseline"] = {"value": n_ref / tref, "unit": UNIT, "cores": cores, "kind": "reference",
+                                        "sample": f"{n_ref} shots of the same workload (host sampler seed 1234), the unmodified reference "
+                                                  f"(baseline/_ref, decoders.MS_decoder X+Z called as simulator.py:278-279), {cores} worker processes",
+                                        "port": port}
+            else:
+                line["cpu_baseline"] = port
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

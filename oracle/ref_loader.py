@@ -22,7 +22,17 @@ import types
 
 import numpy as np
 
-REF_DIR = os.environ.get("QLDPC_REF_DIR", "/root/reference")
+def _find_ref_dir() -> str:
+    """QLDPC_REF_DIR, else the read-only tree of the build container, else the pip-installed copy that travels to the GPU box
+    (baseline/_ref, produced by baseline/install_reference.sh; the package only -- no data/ directory)."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for d in (os.environ.get("QLDPC_REF_DIR"), "/root/reference", os.path.join(here, "baseline", "_ref")):
+        if d and os.path.isfile(os.path.join(d, "qLDPCsim", "decoders.py")):
+            return d
+    return os.environ.get("QLDPC_REF_DIR", "/root/reference")
+
+
+REF_DIR = _find_ref_dir()
 
 
 def available() -> bool:
@@ -75,6 +85,8 @@ class _Inert:
 
     def sample(self, shots):
         rec = _Inert.record
+        if isinstance(rec, list):            # a sweep (simulate() calls simulate_p once per p): one record per call, in order
+            rec = rec.pop(0)
         assert rec is not None and rec.shape[0] == shots
         return rec
 
@@ -87,5 +99,5 @@ def load_simulator(record: np.ndarray):
     stim.PauliString = types.SimpleNamespace(from_numpy=lambda **k: None)
     stim.Tableau = types.SimpleNamespace(from_stabilizers=lambda *a, **k: _Inert())
     sys.modules["stim"] = stim
-    _Inert.record = np.asarray(record, dtype=bool)
+    _Inert.record = [np.asarray(r, dtype=bool) for r in record] if isinstance(record, list) else np.asarray(record, dtype=bool)
     return load("simulator")
