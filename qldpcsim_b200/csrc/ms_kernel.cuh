@@ -22,8 +22,10 @@
 //   * check phase: LPC = 1, 2, 4 or 8 lanes share one check (chosen per layer so that the layer fills the
 //     warp); min / second min are taken on the ROUNDED per-edge values in binary32 (see ms_check_phase); rows shorter
 //     than the instantiated row weight are filled with padding edges whose posterior is +inf (no predicates);
-//   * variable phase: lane <-> two variables adjacent to the layer per trip, re-summing ALL their c2v in
-//     ascending check order in binary32 (decoders.py:172).  Layers need not be column-disjoint
+//   * variable phase: lane <-> two / four variables adjacent to the layer per trip, re-summing ALL their c2v in
+//     ascending check order in binary32 (decoders.py:172).  The plan lists a layer's LOW-DEGREE variables first (degree <=
+//     DMIN, 62 % of the edges of the lifted-product codes: column weights 3 and 5) in fixed positions of every quad trip, where
+//     they are summed with DMIN loads and no degree guards instead of DV loads and DV - DMIN selects (ms_colsum4).  Layers need not be column-disjoint
 //     (simulator.py:230-234 hands the decoder the partition of the OTHER matrix), so the two phases are
 //     separated by a warp barrier;
 //   * hard decision: fl64(L + S_j) < 0  <=>  S_j < Tf with Tf = L negated and rounded UP to binary32 (the
@@ -76,7 +78,8 @@ struct MsTables {
                          //               the second sub-group of the step's LAST pair-trip is empty (a single-variable trip is run
                          //               instead), number of sub-layers of a merged step (0: plain layer), 0}
     int off_layer_chk;   // u16 [...]     check indices, layer by layer
-    int off_lvar;        // u32 [...]     lo16 = 4*j'_a, hi16 = 4*j'_b: the two variables of (trip, lane); dummy = 4*n
+    int off_lvar;        // u32 [...]     lo16 = 4*j'_a, hi16 = 4*j'_b: the two variables of (trip, lane); dummy = 4*n.  With
+                         //               0 < DMIN < DV the FIRST entry of a quad trip (two consecutive entries) holds variables of degree <= DMIN only
     int off_lsub;        // u16 [...]     parallel to lvar: lo8 / hi8 = sub-layer (within its merged step) of variable a / b
     int off_col_ptr;     // u16 [n+2]     CSC pointers in the renumbering (variable n: empty)
     int off_col_chk;     // u16 [E]       checks of j', ascending
@@ -224,6 +227,25 @@ __device__ __forceinline__ float ms_colsum(uint32_t c2vj /* c2v + 4*j' */, uint3
     return s;
 }
 
+// New sums of the four variables of a quad trip.  When only some regions hold every variable (0 < DMIN < DV) the plan fills the
+// first two sub-groups of every quad with variables of degree <= DMIN (or dummies) only: they are summed with DMIN loads and
+// no degree guards -- a static property of the list layout, no per-trip test (ms_plan.h: var_cost).
+template <int DV, int DMIN, bool LOW>
+__device__ __forceinline__ float ms_colsum_sel(uint32_t j4, const MsAddr &A, const MsTables &t)
+{
+    if constexpr (LOW && DMIN > 0 && DMIN < DV) return ms_colsum<DMIN, DMIN>(A.c2v + j4, j4, t);
+    else return ms_colsum<DV, DMIN>(A.c2v + j4, j4, t);
+}
+
+template <int DV, int DMIN>
+__device__ __forceinline__ void ms_colsum4(const uint32_t (&j4)[4], const MsAddr &A, const MsTables &t, float (&s)[4])
+{
+    s[0] = ms_colsum_sel<DV, DMIN, true>(j4[0], A, t);
+    s[1] = ms_colsum_sel<DV, DMIN, true>(j4[1], A, t);
+    s[2] = ms_colsum_sel<DV, DMIN, false>(j4[2], A, t);
+    s[3] = ms_colsum_sel<DV, DMIN, false>(j4[3], A, t);
+}
+
 // Cooperative parity update for the variables whose hard decision flipped (rare; one flipped variable per trip).
 __device__ __forceinline__ void ms_apply_flips(uint32_t flips, uint32_t j4, int lane, const MsAddr &A, int &delta)
 {
@@ -282,8 +304,7 @@ __device__ __forceinline__ void ms_var_update4(uint32_t e0, uint32_t e1, int lan
     float s_old[4], s[4];
 #pragma unroll
     for (int v = 0; v < 4; ++v) s_old[v] = sld_f32(A.S + j4[v]);
-#pragma unroll
-    for (int v = 0; v < 4; ++v) s[v] = ms_colsum<DV, DMIN>(A.c2v + j4[v], j4[v], t);
+    ms_colsum4<DV, DMIN>(j4, A, t, s);
     uint32_t f[4];
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
@@ -433,8 +454,12 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
                     float s_old[4], s_new[4];
 #pragma unroll
                     for (int v = 0; v < 4; ++v) s_old[v] = sld_f32(A.S + j4[v]);
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) s_new[v] = ms_colsum<DV, DMIN>(A.c2v + j4[v], j4[v], t);
+                    if (h1) ms_colsum4<DV, DMIN>(j4, A, t, s_new);             // a whole quad: [low, low, any, any]
+                    else {                                                     // a lone pair-trip is generic (the other two are dummies)
+                        s_new[0] = ms_colsum<DV, DMIN>(A.c2v + j4[0], j4[0], t);
+                        s_new[1] = ms_colsum<DV, DMIN>(A.c2v + j4[1], j4[1], t);
+                        s_new[2] = s_old[2]; s_new[3] = s_old[3];
+                    }
                     uint32_t f[4];
                     int F = 0;
 #pragma unroll

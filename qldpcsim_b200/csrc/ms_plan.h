@@ -35,6 +35,7 @@ struct MsPlanLayout {
     std::vector<int> slot_edge;            // [m][dc_inst] CSR edge in slot k of check i, -1 = padding
     std::vector<int> lvar_ptr;             // [nl+1] in packed entries (32 per trip)
     std::vector<uint32_t> lvar;            // packed (4*j'_a) | (4*j'_b << 16); dummy = 4*n
+    int sub_total = 0, sub_min = 0;        // sub-groups listed (whole pair-trips) with / without the [low, low, any, any] quad pattern
     long long wavefronts = 0, ideal = 0;   // per full iteration over all layers (check phase: S load + c2v load + c2v store;
                                            // variable phase: S load + S store + dv_inst c2v loads per sub-group)
     int search_evals = 0;
@@ -130,7 +131,12 @@ struct Evaluator {
     }
 
     // variable groups of layer l: the variables of each residue class (j' mod 32) are dealt to the sub-groups holding the
-    // fewest of that class
+    // fewest of that class.  QUAD PATTERN [low, low, any, any]: variables whose degree does not exceed `dmin` (the number of
+    // leading regions that hold every variable) only have terms in those regions, so a sub-group made of such variables alone
+    // is summed with dmin loads and no degree guards.  When 0 < dmin < dv_inst the kernel treats the first two sub-groups of
+    // EVERY quad trip (two consecutive pair-trips) that way -- statically, without a per-trip test -- so the plan must put
+    // low-degree variables (or dummies) only there; the last pair-trip of an odd count stays generic.  On the lifted-product
+    // codes (column weights 3 and 5, five low and three high variables per check) this costs no extra trips.
     long long var_cost(int l, bool store, long long *ideal) const
     {
         std::vector<int> vs;
@@ -142,37 +148,69 @@ struct Evaluator {
         vs.erase(std::unique(vs.begin(), vs.end()), vs.end());
         // as few sub-groups as possible (an instruction stream per sub-group costs more than a two-way bank conflict); the list
         // is padded to whole pair-trips with an empty sub-group, which the kernel skips (single-variable trip)
-        const int V = (int)vs.size(), Gfill = (V + 31) / 32, G = (Gfill + 1) & ~1;
+        const int V = (int)vs.size();
+        const bool pattern = L.dmin > 0 && L.dmin < L.dv_inst;
+        const int low_from = pattern ? L.cnt[L.dmin] : 0;               // j' >= low_from: degree <= dmin (descending-degree numbering)
+        std::vector<int> low, rest;
+        for (int jp : vs) ((pattern && jp >= low_from) ? low : rest).push_back(jp);
+        int G = (((V + 31) / 32) + 1) & ~1;                             // sub-groups, whole pair-trips
+        auto low_only = [&](int g2, int G2) { return pattern && g2 < 4 * (G2 / 4) && (g2 & 3) < 2; };   // position in the layer's list
+        if (pattern) {
+            for (;; G += 2) {                                           // enough room for the high-degree variables outside the low-only slots
+                const int nlow_groups = 2 * (G / 4);
+                const int placed_low = std::min((int)low.size(), 32 * nlow_groups);
+                if (V - placed_low <= 32 * (G - nlow_groups)) break;
+            }
+        }
+        if (store) { const_cast<MsPlanLayout &>(L).sub_total += G; const_cast<MsPlanLayout &>(L).sub_min += (((V + 31) / 32) + 1) & ~1; }
         std::vector<std::vector<int>> sub(G);
         std::vector<int> res_cnt((size_t)G * 32, 0);
-        std::vector<std::vector<int>> by_res(32);
-        for (int jp : vs) by_res[jp & 31].push_back(jp);
         // Sub-groups are filled one after the other.  Each takes one variable of every residue class that still has some
         // (largest classes first), which is conflict-free; only when the sub-groups behind it could not hold the rest does
         // it take second, third ... members of the largest classes.  Unavoidable conflicts thus end up concentrated in few
-        // sub-groups instead of being spread over all of them.
-        int remaining = V;
-        for (int g2 = 0; g2 < Gfill; ++g2) {
-            const int need = std::min(32, std::max(0, remaining - 32 * (Gfill - g2 - 1)));
-            int taken = 0;
-            for (int round = 0; round < 32 && (round == 0 || taken < need); ++round) {
-                int rs[32];
-                for (int r = 0; r < 32; ++r) rs[r] = r;
-                std::stable_sort(rs, rs + 32, [&](int a2, int b2) { return by_res[a2].size() > by_res[b2].size(); });
-                for (int ri = 0; ri < 32 && taken < 32; ++ri) {
-                    const int r = rs[ri];
-                    if (by_res[r].empty() || (round > 0 && taken >= need)) continue;
-                    sub[g2].push_back(by_res[r].back());
-                    by_res[r].pop_back();
-                    res_cnt[(size_t)g2 * 32 + r]++;
-                    ++taken;
+        // sub-groups instead of being spread over all of them.  Returns the variables it could not place.
+        auto deal = [&](const std::vector<int> &vars, const std::vector<int> &groups) {
+            std::vector<std::vector<int>> by_res(32);
+            for (int jp : vars) by_res[jp & 31].push_back(jp);
+            int remaining = (int)vars.size();
+            const int gc = (int)groups.size();
+            for (int gi = 0; gi < gc; ++gi) {
+                const int need = std::min(32, std::max(0, remaining - 32 * (gc - gi - 1)));
+                int taken = 0;
+                for (int round = 0; round < 32 && (round == 0 || taken < need); ++round) {
+                    int rs[32];
+                    for (int r = 0; r < 32; ++r) rs[r] = r;
+                    std::stable_sort(rs, rs + 32, [&](int a2, int b2) { return by_res[a2].size() > by_res[b2].size(); });
+                    for (int ri = 0; ri < 32 && taken < 32; ++ri) {
+                        const int r = rs[ri];
+                        if (by_res[r].empty() || (round > 0 && taken >= need)) continue;
+                        sub[groups[gi]].push_back(by_res[r].back());
+                        by_res[r].pop_back();
+                        res_cnt[(size_t)groups[gi] * 32 + r]++;
+                        ++taken;
+                    }
                 }
+                remaining -= taken;
             }
-            remaining -= taken;
+            std::vector<int> left;
+            for (int r = 0; r < 32; ++r) for (int jp : by_res[r]) left.push_back(jp);
+            return left;
+        };
+        {
+            std::vector<int> g_low, g_any;
+            for (int g2 = 0; g2 < G; ++g2) (low_only(g2, G) ? g_low : g_any).push_back(g2);
+            std::vector<int> left = deal(low, g_low);
+            rest.insert(rest.end(), left.begin(), left.end());
+            std::sort(rest.begin(), rest.end());
+            // the generic sub-groups are filled front to back; trailing ones may stay empty (skipped as a single-variable trip)
+            const int need_any = ((int)rest.size() + 31) / 32;
+            g_any.resize(std::max(need_any, 0));
+            deal(rest, g_any);
         }
         long long cost = 0;
-        const int per = 2 + L.dv_inst;
-        for (int g2 = 0; g2 < Gfill; ++g2) {
+        for (int g2 = 0; g2 < G; ++g2) {
+            if (sub[g2].empty() && !low_only(g2, G)) continue;
+            const int per = 2 + (low_only(g2, G) ? L.dmin : L.dv_inst);
             int mx = 0;
             for (int r = 0; r < 32; ++r) mx = std::max(mx, res_cnt[(size_t)g2 * 32 + r]);
             cost += (long long)per * std::max(mx, 1);
@@ -200,6 +238,7 @@ struct Evaluator {
             L.slot_edge.assign((size_t)g.m * L.dc_inst, -1);
             L.lvar.clear();
             L.lvar_ptr.assign(g.nl + 1, 0);
+            L.sub_total = L.sub_min = 0;
             // checks outside every layer keep the ascending order (never executed, but the table stays well defined)
             for (int i = 0; i < g.m; ++i)
                 for (int x = g.row_ptr[i]; x < g.row_ptr[i + 1]; ++x) L.slot_edge[(size_t)i * L.dc_inst + (x - g.row_ptr[i])] = x;

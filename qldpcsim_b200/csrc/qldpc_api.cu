@@ -364,6 +364,16 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             MsGraphView gv{m, n, E, p->row_ptr.data(), p->col_idx.data(), p->col_ptr.data(), p->row_idx.data(), nsteps, step_ptr.data(), p->layer_chk.data()};
             MsPlanLayout pl;
             ms_plan_layout(gv, dc_inst, dv_inst, dmin, /*search=*/true, pl, W);
+            if (dmin > 0 && dmin < dv_inst && 100ll * pl.sub_total > 115ll * pl.sub_min) {
+                // the [low, low, any, any] quad pattern of the partially guarded instances needs too many padding sub-groups on this
+                // graph (few variables of degree <= dmin): use the instance that guards every region instead
+                full_regions = 0;
+                pk->ms_full_regions = 0;
+                int a1, a2;
+                pk->ms = ms_select(dc, dv, 0, W == 2 ? 2 : 0, spec, &a1, &a2, &dmin);
+                pl = MsPlanLayout();
+                ms_plan_layout(gv, dc_inst, dv_inst, dmin, /*search=*/true, pl, W);
+            }
             p->plan_wavefronts = pl.wavefronts; p->plan_wavefronts_ideal = pl.ideal;
             mt.m = m; mt.n = n; mt.E = E; mt.dc = dc_inst; mt.dv = dv; mt.nl = nsteps; mt.mw = t.mw; mt.nw = t.nw;
             mt.n_pad = (n + 63) & ~63;
@@ -395,7 +405,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
                 r[0] = (uint16_t)step_ptr[l]; r[1] = (uint16_t)step_ptr[l + 1]; r[2] = (uint16_t)pl.lpc[l];
                 r[3] = (uint16_t)pl.lvar_ptr[l]; r[4] = (uint16_t)pl.lvar_ptr[l + 1];
                 bool single = pl.lvar_ptr[l + 1] > pl.lvar_ptr[l];
-                for (int x = pl.lvar_ptr[l + 1] - 32; single && x < pl.lvar_ptr[l + 1]; ++x) single = (pl.lvar[x] >> 16) == 4u * (uint32_t)n;
+                for (int x = pl.lvar_ptr[l + 1] - 32; single && x < pl.lvar_ptr[l + 1]; ++x) single = ((pl.lvar[x] >> 16) & 0xfffcu) == 4u * (uint32_t)n;
                 r[5] = single ? 1 : 0;
                 r[6] = (uint16_t)(grp[l + 1] - grp[l] > 1 ? grp[l + 1] - grp[l] : 0);
                 if (r[6] && pl.lvar_ptr[l + 1] - pl.lvar_ptr[l] > 64 * W) return bail(QLDPC_EINVAL, "internal: merged step exceeds one quad trip per warp");

@@ -80,7 +80,7 @@ def test_layout_is_consistent(planner, code, sched):
         assert stats[0] >= stats[1] > 0 and stats[0] <= stats[5]
 
 
-@pytest.mark.parametrize("code,bound", [("LP118_0", 1.12), ("LP118_2", 1.08), ("T", 1.10)])
+@pytest.mark.parametrize("code,bound", [("LP118_0", 1.12), ("LP118_2", 1.10), ("T", 1.10)])
 def test_layered_lifted_codes_are_nearly_conflict_free(planner, code, bound):
     Hx, Hz = [(h % 2).astype(np.int8) for h in pcmlibrary.by_name(code)]
     lX, lZ = pcm.schedule_layers(Hx, Hz, "L")
