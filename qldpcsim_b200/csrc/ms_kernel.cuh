@@ -81,8 +81,8 @@ struct MsTables {
     int off_lvar;        // u32 [...]     lo16 = 4*j'_a, hi16 = 4*j'_b: the two variables of (trip, lane); dummy = 4*n.  With
                          //               0 < DMIN < DV the FIRST entry of a quad trip (two consecutive entries) holds variables of degree <= DMIN only
     int off_lsub;        // u16 [...]     parallel to lvar: lo8 / hi8 = sub-layer (within its merged step) of variable a / b
-    int off_col_ptr;     // u16 [n+2]     CSC pointers in the renumbering (variable n: empty)
-    int off_col_chk;     // u16 [E]       checks of j', ascending
+    int off_col_chk;     // u16 [n+1][DV] checks of j' (flip handling), fixed stride DV = instantiated column weight, 0xFFFF past the
+                         //               degree (variable n: all 0xFFFF)
     int off_rowpar;      // u32 [mw]      parity of the row weights as bit words
     int off_unperm;      // u16 [32*nw]   4*j' of original variable j (4*n past the end)
     int len;             // blob length in uint16 units (multiple of 8)
@@ -132,7 +132,7 @@ __device__ __forceinline__ uint32_t satom_xor(uint32_t a, uint32_t v) { uint32_t
 struct MsAddr {          // shared-window byte addresses, warp-uniform
     uint32_t chk;        // u32 [dc*ms]   (CTA tables)
     uint32_t layer_chk;  // u16 [...]
-    uint32_t col_ptr, col_chk;
+    uint32_t col_chk;
     uint32_t c2v, S, par, syn;   // per-warp state
     uint32_t m4;         // 4*ms : byte stride of one slot row in chk
 };
@@ -246,20 +246,22 @@ __device__ __forceinline__ void ms_colsum4(const uint32_t (&j4)[4], const MsAddr
     s[3] = ms_colsum_sel<DV, DMIN, false>(j4[3], A, t);
 }
 
-// Cooperative parity update for the variables whose hard decision flipped (rare; one flipped variable per trip).
+// Cooperative parity update for the variables whose hard decision flipped (rare; one flipped variable per trip).  The checks of
+// variable j' sit in a fixed-stride table (DV entries per variable, 0xFFFF past its degree): lane x < DV toggles the x-th one.
+template <int DV>
 __device__ __forceinline__ void ms_apply_flips(uint32_t flips, uint32_t j4, int lane, const MsAddr &A, int &delta)
 {
     while (flips) {
         const int src = __ffs(flips) - 1;
         flips &= flips - 1;
-        const uint32_t jf2 = __shfl_sync(0xffffffffu, j4, src) >> 1;            // 2*j': byte offset into the u16 pointer table
-        const uint32_t x0 = sld_u16(A.col_ptr + jf2), x1 = sld_u16(A.col_ptr + jf2 + 2u);
-        const uint32_t x = x0 + lane;
-        if (x < x1) {                                                            // lane <-> check of the flipped variable
-            const uint32_t ch = sld_u16(A.col_chk + 2u * x);
-            const uint32_t bit = 1u << (ch & 31u);
-            const uint32_t old = satom_xor(A.par + 4u * (ch >> 5), bit);
-            delta += (old & bit) ? -1 : 1;
+        const uint32_t jf4 = __shfl_sync(0xffffffffu, j4, src);
+        if (lane < DV) {                                                         // lane <-> check of the flipped variable
+            const uint32_t ch = sld_u16(A.col_chk + (jf4 >> 1) * (uint32_t)DV + 2u * (uint32_t)lane);
+            if (ch != 0xffffu) {
+                const uint32_t bit = 1u << (ch & 31u);
+                const uint32_t old = satom_xor(A.par + 4u * (ch >> 5), bit);
+                delta += (old & bit) ? -1 : 1;
+            }
         }
     }
 }
@@ -278,8 +280,8 @@ __device__ __forceinline__ void ms_var_update2(uint32_t ja4, uint32_t jb4, int l
     const uint32_t fa = __ballot_sync(0xffffffffu, (a < Tf) != (a_old < Tf));   // hard decision flipped (:173-174)
     const uint32_t fb = __ballot_sync(0xffffffffu, (b < Tf) != (b_old < Tf));
     if (fa | fb) {
-        ms_apply_flips(fa, ja4, lane, A, delta);
-        ms_apply_flips(fb, jb4, lane, A, delta);
+        ms_apply_flips<DV>(fa, ja4, lane, A, delta);
+        ms_apply_flips<DV>(fb, jb4, lane, A, delta);
     }
 }
 
@@ -292,7 +294,7 @@ __device__ __forceinline__ void ms_var_update1(uint32_t ja4, int lane, const MsA
     const float a = ms_colsum<DV, DMIN>(A.c2v + ja4, ja4, t);
     sst_f32(sa, a);
     const uint32_t fa = __ballot_sync(0xffffffffu, (a < Tf) != (a_old < Tf));   // hard decision flipped (:173-174)
-    if (fa) ms_apply_flips(fa, ja4, lane, A, delta);
+    if (fa) ms_apply_flips<DV>(fa, ja4, lane, A, delta);
 }
 
 // Same with FOUR variables per lane (two consecutive pair-trips of the layer's list at once): more independent chains in
@@ -313,7 +315,7 @@ __device__ __forceinline__ void ms_var_update4(uint32_t e0, uint32_t e1, int lan
     }
     if (f[0] | f[1] | f[2] | f[3]) {
 #pragma unroll
-        for (int v = 0; v < 4; ++v) ms_apply_flips(f[v], j4[v], lane, A, delta);
+        for (int v = 0; v < 4; ++v) ms_apply_flips<DV>(f[v], j4[v], lane, A, delta);
     }
 }
 
@@ -353,7 +355,6 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
     MsAddr A;
     A.chk = tab + 2u * t.off_chk;
     A.layer_chk = tab + 2u * t.off_layer_chk;
-    A.col_ptr = tab + 2u * t.off_col_ptr;
     A.col_chk = tab + 2u * t.off_col_chk;
     A.c2v = wbase + lay.off_c2v;
     A.S = wbase + lay.off_S;
@@ -494,7 +495,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
                         int delta = 0;
                         if (F) {
 #pragma unroll
-                            for (int v = 0; v < 4; ++v) ms_apply_flips(f[v], j4[v], lane, A, delta);
+                            for (int v = 0; v < 4; ++v) ms_apply_flips<DV>(f[v], j4[v], lane, A, delta);
                         }
                         settle(delta);
                     } else {
@@ -512,7 +513,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
 #pragma unroll
                             for (int v = 0; v < 4; ++v) {
                                 const uint32_t mk = __ballot_sync(full, ((f[v] >> lane) & 1u) && kk[v] == k);
-                                ms_apply_flips(mk, j4[v], lane, A, delta);
+                                ms_apply_flips<DV>(mk, j4[v], lane, A, delta);
                             }
                             settle(delta);
                             if constexpr (W > 1) team_sync();              // every warp has read the count before the next round adds to it

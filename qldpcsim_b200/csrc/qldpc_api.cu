@@ -429,18 +429,12 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
                     }
                 }
             }
-            // CSC in the renumbering (flip handling)
-            mt.off_col_ptr = put(n + 2);
-            mt.off_col_chk = put(E);
-            {
-                int pos = 0;
-                for (int jp = 0; jp < n; ++jp) {
-                    b[mt.off_col_ptr + jp] = (uint16_t)pos;
-                    const int j = pl.order[jp];
-                    for (int x = p->col_ptr[j]; x < p->col_ptr[j + 1]; ++x) b[mt.off_col_chk + pos++] = (uint16_t)p->row_idx[x];
-                }
-                b[mt.off_col_ptr + n] = (uint16_t)pos;
-                b[mt.off_col_ptr + n + 1] = (uint16_t)pos;
+            // checks of every variable in the renumbering, fixed stride (flip handling)
+            mt.off_col_chk = put((n + 1) * dv_inst);
+            std::fill(b.begin() + mt.off_col_chk, b.begin() + mt.off_col_chk + (n + 1) * dv_inst, (uint16_t)0xFFFF);
+            for (int jp = 0; jp < n; ++jp) {
+                const int j = pl.order[jp];
+                for (int x = p->col_ptr[j]; x < p->col_ptr[j + 1]; ++x) b[mt.off_col_chk + jp * dv_inst + (x - p->col_ptr[j])] = (uint16_t)p->row_idx[x];
             }
             mt.off_rowpar = put32(t.mw);
             {
