@@ -10,7 +10,9 @@
 //   4. information bits keep the decoder's hard decision -- for order 1 the first information bit is flipped,
 //      for order 0 and >= 2 none (the reference's order loop aliases its buffers, App. B-8) -- and the basis
 //      bits are the unique solution of H_J e_J = s + H_I e_I                           (decoders.py:347-368)
-// Implementation: the matrix is NOT permuted; rows stay bit-packed in original column numbering with one
+// TWO KERNELS.  osd_reg_kernel<W> (below, the one every code of the reference's library uses: m <= 512 checks, n <= 1152
+// columns) keeps one ROW PER THREAD IN REGISTERS, in permuted column order; osd_kernel<TRIPS> is the shared-memory formulation
+// for larger matrices.  Implementation of osd_kernel: the matrix is NOT permuted; rows stay bit-packed in original column numbering with one
 // extra word for the right-hand side, initialised to the residual syndrome s + H e.  Solving for the basis
 // FLIPS d_J (H_J d_J = residual) is equivalent and needs no knowledge of I before the elimination.
 //   * FORWARD elimination only (the pivot column is cleared from the rows that are not pivot rows yet), then a
@@ -30,6 +32,7 @@ namespace qldpc {
 
 struct OsdArgs {
     int m, n, mw, nw;
+    const int32_t *row_ptr, *col_idx;   // CSR of H (osd_reg_kernel builds its permuted rows from it)
     const uint32_t *hbits;     // [m][nw]
     uint32_t *ehat;            // [*][nw] in/out
     const uint32_t *syn;       // [*][mw]
@@ -244,8 +247,220 @@ __global__ void __launch_bounds__(kOsdThreads) osd_kernel(OsdArgs a)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// osd_reg_kernel<W>: Gauss-Jordan with the matrix in REGISTERS.
+//   * thread i owns row i of H, permuted into reliability order (bit c' of the row = H[i][perm[c']]), as W 32-bit registers
+//     plus the right-hand-side bit; the rows are built from the CSR lists (8 entries per row on the lifted-product codes)
+//     through the inverse permutation, not by gathering n bits;
+//   * column order: bitonic sort of (reliability bits, index) in shared memory -- the stable order of the library (a
+//     caller-supplied permutation replaces it);
+//   * the column walk is unrolled over the W words of a row, so every register index is static.  Inside word k: the OR over the
+//     unused rows of (word k & columns not yet examined) -- a warp REDUX, one shared word per warp, barrier -- tells every
+//     thread the next pivot column (lowest set bit; the clear bits below it are information columns) or that the word is
+//     exhausted; the pivot row is the first unused row holding that bit (first such warp, first such lane); it publishes its
+//     words k..W-1 and its right-hand side, barrier, and EVERY other row holding the bit -- used or not: Gauss-Jordan, so no
+//     back-substitution -- XORs them in.  Words below k are never needed again (only pivot columns and the right-hand side
+//     enter the solution), so the work per pivot shrinks as the walk advances;
+//   * two CTA barriers and ~2 (W - k) + 25 instructions per thread and pivot, against ~40 instructions per ROW and pivot in
+//     the shared-memory formulation: 10 x fewer instructions per solve, 10 x shorter latency per solve;
+//   * solution: pivot row p gives flip(perm[col_p]) = rhs_p (+ bit of the first information column for order 1, App. B-8).
+// Same unique solution as any elimination given the column order (bit-exact with the oracle and the reference goldens).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kOsdRegMaxThreads = 512;
+
+inline size_t osd_reg_smem_bytes(int n, int nw, int W)
+{
+    int np = 1;
+    while (np < n) np <<= 1;
+    size_t b = (size_t)np * 8;            // sort keys
+    b += (size_t)np * 4;                  // sorted indices = perm
+    b += (((size_t)n * 2 + 15) & ~size_t(15));   // inverse permutation (u16)
+    b += (size_t)(W + 4) * 4;             // published pivot row + right-hand side
+    b += 32 * 4;                          // per-warp OR words
+    b += (size_t)nw * 4;                  // the shot's estimate words
+    return b + 64;
+}
+
+template <int W>
+struct OsdWalk {
+    uint32_t row[W];      // my row, permuted column order
+    uint32_t rhs;         // right-hand-side bit
+    bool used;            // my row is a pivot row (or lies beyond m)
+    int mycol;            // permuted column my row is the pivot of, or -1
+    int rank, first_info, last_piv;
+    uint32_t fbit;        // my row's bit in the first information column
+};
+
+// Word K of the column walk (see osd_reg_kernel); recursion on K keeps every register index static.
+template <int W, int K>
+__device__ __forceinline__ void osd_walk(OsdWalk<W> &st, int rank_h, int n, int lane, int warp, int nwarps, uint32_t *P, uint32_t *wor)
+{
+    static_assert(W % 4 == 0, "rows are published and read back as 128-bit vectors");
+    const unsigned full = 0xffffffffu;
+    constexpr int K4 = K & ~3;                                                // first word of the vector that holds word K
+    if (st.rank < rank_h && 32 * K < n) {
+        uint32_t cmask = (n - 32 * K >= 32) ? full : ((1u << (n - 32 * K)) - 1u);      // columns of this word not examined yet
+        while (st.rank < rank_h) {
+            const uint32_t wo = __reduce_or_sync(full, st.used ? 0u : (st.row[K] & cmask));
+            if (lane == 0) wor[warp] = wo;
+            __syncthreads();
+            const uint32_t wv = lane < nwarps ? wor[lane] : 0u;              // lane x <-> warp x (at most 16 warps)
+            const uint32_t live = __reduce_or_sync(full, wv);
+            const uint32_t below = live ? (cmask & ((live & (0u - live)) - 1u)) : cmask;   // information columns passed over
+            if (st.first_info < 0 && below) {
+                const int c0 = __ffs(below) - 1;
+                st.first_info = 32 * K + c0;
+                st.fbit = (st.row[K] >> c0) & 1u;
+            }
+            if (!live) { __syncthreads(); break; }                          // word exhausted (wor is rewritten after this barrier)
+            const int c = __ffs(live) - 1;
+            const uint32_t bit = 1u << c;
+            const int pw = __ffs(__ballot_sync(full, (wv & bit) != 0u)) - 1;   // first warp with an unused row holding the column
+            const bool has = (st.row[K] & bit) != 0u;
+            const uint32_t cand = __ballot_sync(full, has && !st.used);
+            const bool is_piv = warp == pw && has && !st.used && lane == __ffs(cand) - 1;
+            if (is_piv) {
+#pragma unroll
+                for (int w = K4; w < W; w += 4) *reinterpret_cast<uint4 *>(P + w) = make_uint4(st.row[w], st.row[w + 1], st.row[w + 2], st.row[w + 3]);
+                P[W] = st.rhs;
+                st.used = true;
+                st.mycol = 32 * K + c;
+            }
+            __syncthreads();
+            if (has && !is_piv) {                                            // words K4 .. K-1 are dead: XOR-ing them as well is harmless
+#pragma unroll
+                for (int w = K4; w < W; w += 4) {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(P + w);
+                    st.row[w] ^= q.x; st.row[w + 1] ^= q.y; st.row[w + 2] ^= q.z; st.row[w + 3] ^= q.w;
+                }
+                st.rhs ^= P[W];
+            }
+            cmask &= ~(bit | (bit - 1u));
+            st.last_piv = 32 * K + c;
+            ++st.rank;
+        }
+    }
+    if constexpr (K + 1 < W) osd_walk<W, K + 1>(st, rank_h, n, lane, warp, nwarps, P, wor);
+}
+
+template <int W, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) osd_reg_kernel(OsdArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int m = a.m, n = a.n, nw = a.nw;
+    int np = 1;
+    while (np < n) np <<= 1;
+    unsigned long long *key = reinterpret_cast<unsigned long long *>(smem);
+    int *perm = reinterpret_cast<int *>(smem + (size_t)np * 8);
+    uint16_t *pos = reinterpret_cast<uint16_t *>(smem + (size_t)np * 12);
+    uint32_t *P = reinterpret_cast<uint32_t *>(smem + (size_t)np * 12 + (((size_t)n * 2 + 15) & ~size_t(15)));   // 16-byte aligned
+    uint32_t *wor = P + (W + 4);
+    uint32_t *eb = wor + 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x, nwarps = T >> 5;
+    const unsigned full = 0xffffffffu;
+    const int count = a.count_dev ? min(*a.count_dev, a.count) : a.count;
+    const bool valid = tid < m;
+
+    for (int item = blockIdx.x; item < count; item += gridDim.x) {
+        const long long shot = a.shot_ids ? a.shot_ids[item] : item;
+        uint32_t *e = a.ehat + shot * nw;
+        const uint32_t *s = a.syn + shot * a.mw;
+        // ---- column order
+        if (a.perm) {
+            const int32_t *pp = a.perm + (long long)item * n;
+            for (int j = tid; j < n; j += T) perm[j] = pp[j];
+        } else {
+            const double *llr = a.llr + (long long)item * n;
+            for (int j = tid; j < np; j += T) {
+                key[j] = j < n ? (unsigned long long)__double_as_longlong(osd_reliability(llr[j])) : ~0ull;   // rel in [0.5, 1]: bit order = value order
+                perm[j] = j;
+            }
+            __syncthreads();
+            for (int k2 = 2; k2 <= np; k2 <<= 1)
+                for (int j = k2 >> 1; j > 0; j >>= 1) {
+                    for (int t = tid; t < (np >> 1); t += T) {
+                        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
+                        const unsigned long long ka = key[lo], kb = key[hi];
+                        const int ia = perm[lo], ib = perm[hi];
+                        const bool gt = ka > kb || (ka == kb && ia > ib);          // ties by index: the stable order
+                        if (gt == ((lo & k2) == 0)) { key[lo] = kb; key[hi] = ka; perm[lo] = ib; perm[hi] = ia; }
+                    }
+                    __syncthreads();
+                }
+        }
+        for (int w = tid; w < nw; w += T) eb[w] = e[w];
+        __syncthreads();
+        for (int c = tid; c < n; c += T) pos[perm[c]] = (uint16_t)c;
+        __syncthreads();
+        // ---- my row in permuted column order, residual right-hand side s + H e
+        uint32_t row[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) row[w] = 0u;
+        uint32_t rhs = 0;
+        if (valid) {
+            rhs = (s[tid >> 5] >> (tid & 31)) & 1u;
+            for (int x = a.row_ptr[tid]; x < a.row_ptr[tid + 1]; ++x) {
+                const int j = a.col_idx[x];
+                rhs ^= (eb[j >> 5] >> (j & 31)) & 1u;
+                const uint32_t c = pos[j], cw = c >> 5, bit = 1u << (c & 31u);
+#pragma unroll
+                for (int w = 0; w < W; ++w) row[w] |= (cw == (uint32_t)w) ? bit : 0u;
+            }
+        }
+        // ---- Gauss-Jordan over the columns in order (osd_walk: one instantiation per word of a row, static register indices)
+        OsdWalk<W> st;
+#pragma unroll
+        for (int w = 0; w < W; ++w) st.row[w] = row[w];
+        st.rhs = rhs; st.used = !valid; st.mycol = -1; st.rank = 0; st.first_info = -1; st.last_piv = -1; st.fbit = 0;
+        osd_walk<W, 0>(st, a.rank_h, n, lane, warp, nwarps, P, wor);
+#pragma unroll
+        for (int w = 0; w < W; ++w) row[w] = st.row[w];
+        rhs = st.rhs;
+        const int mycol = st.mycol, first_info = st.first_info, last_piv = st.last_piv;
+        uint32_t fbit = st.fbit;
+        // ---- order 1: the first information column is flipped (App. B-8)
+        if (a.order == 1) {
+            int f = first_info;
+            if (f < 0 && last_piv + 1 < n) {                                  // no column was passed over: the one after the last pivot
+                f = last_piv + 1;
+                uint32_t wsel = 0;
+#pragma unroll
+                for (int w = 0; w < W; ++w) wsel = ((f >> 5) == w) ? row[w] : wsel;
+                fbit = (wsel >> (f & 31)) & 1u;
+            }
+            if (f >= 0) {
+                if (mycol >= 0) rhs ^= fbit;
+                if (tid == 0) atomicXor(&eb[perm[f] >> 5], 1u << (perm[f] & 31));
+            }
+        }
+        // ---- solution: the flip of a pivot column is the right-hand side of its row
+        if (mycol >= 0 && (rhs & 1u)) { const int col = perm[mycol]; atomicXor(&eb[col >> 5], 1u << (col & 31)); }
+        __syncthreads();
+        for (int w = tid; w < nw; w += T) e[w] = eb[w];
+        __syncthreads();
+    }
+}
+
 inline int osd_launch(const OsdArgs &a, int sm_count, cudaStream_t st)
 {
+    static const int force_old = [] { const char *ev = getenv("QLDPC_OSD_KERNEL"); return ev && ev[0] == 's' ? 1 : 0; }();   // 's': shared-memory kernel (tests)
+    const int threads = ((a.m + 31) / 32) * 32;
+    if (!force_old && threads <= kOsdRegMaxThreads && a.nw <= 36 && a.row_ptr) {
+        // instances: (words per row, launch bound): small rows run four CTAs of 256 threads per SM, the 36-word rows of LP118_2 /
+        // Tanner (450 / 465 checks) one CTA of up to 512
+        const int W = (a.nw <= 8 && threads <= 256) ? 8 : ((a.nw <= 20 && threads <= 256) ? 20 : 36);
+        void (*fn)(OsdArgs) = W == 8 ? osd_reg_kernel<8, 256, 6> : (W == 20 ? osd_reg_kernel<20, 256, 4> : osd_reg_kernel<36, 512, 1>);
+        const size_t smem = osd_reg_smem_bytes(a.n, a.nw, W);
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemPerCta);
+        if (e != cudaSuccess) return (int)e;
+        int per_sm = 1;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem);
+        if (e != cudaSuccess) return (int)e;
+        const int grid = std::max(1, std::min(a.count, sm_count * std::max(1, per_sm)));
+        fn<<<grid, threads, smem, st>>>(a);
+        return (int)cudaGetLastError();
+    }
     const size_t smem = osd_smem_bytes(a.m, a.n, a.nw);
     if (smem > (size_t)kMaxSmemPerCta || a.nw + 1 > 32 * kOsdMaxTrips) return (int)cudaErrorInvalidValue;
     void (*fn)(OsdArgs) = (a.nw + 1 <= 32) ? osd_kernel<1> : osd_kernel<2>;

@@ -749,6 +749,7 @@ static int osd_on_failures(qldpc_plan *p, uint32_t *ehat, const uint32_t *syn, i
     OsdArgs a;
     a.m = p->tab.m; a.n = p->tab.n; a.mw = p->tab.mw; a.nw = p->tab.nw;
     a.hbits = p->d_hbits;
+    a.row_ptr = p->d_row_ptr; a.col_idx = p->d_col_idx;
     a.ehat = ehat; a.syn = syn;
     a.llr = (const double *)p->scratch[1];
     a.perm = nullptr;
@@ -772,6 +773,7 @@ int qldpc_osd(qldpc_plan *p, uint32_t *ehat, const uint32_t *syn, const double *
     OsdArgs a;
     a.m = p->tab.m; a.n = p->tab.n; a.mw = p->tab.mw; a.nw = p->tab.nw;
     a.hbits = p->d_hbits;
+    a.row_ptr = p->d_row_ptr; a.col_idx = p->d_col_idx;
     a.ehat = ehat; a.syn = syn; a.llr = llr; a.perm = perm;
     a.shot_ids = nullptr; a.count_dev = nullptr; a.count = (int)shots; a.order = order; a.rank_h = p->rank_h;
     if (shots == 0) return QLDPC_OK;

@@ -454,3 +454,19 @@ def test_bp_big_reference_goldens_bit_exact(tag, cuda_device):
     out = Decoder(Hz, "BP", p=float(g["p"]) / 3, max_iter=iters, layers=lX).decode(syn)
     same = (out["e_hat"] == e_ref).all(1) & (out["iters"] == it_ref)
     assert same.all(), f"p=0.{tag}: {int((~same).sum())} of {len(same)} decodes differ from the reference"
+
+
+def test_osd_shared_memory_kernel_still_exact(cuda_device):
+    """The register-resident OSD kernel serves every code of the reference's library; the shared-memory formulation remains for
+    larger matrices (more than 512 checks or 1088 columns).  QLDPC_OSD_KERNEL=s forces it: the reference OSD goldens (LP04_0,
+    LP118_0 and -- two words per lane -- LP118_2 / Tanner) must stay bit-exact through it (environment knobs are read once per
+    process, hence the sub-process)."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    env = dict(os.environ, QLDPC_OSD_KERNEL="s")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu", "-k",
+                        "test_golden_osd or (test_osd_config3_size_against_oracle and 700)"], env=env, capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
