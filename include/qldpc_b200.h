@@ -95,6 +95,12 @@ int qldpc_plan_destroy(qldpc_plan *plan);
  * kernel (< n_layers when runs of layers with disjoint variable sets were merged into one step), 17 warps per shot. */
 int64_t qldpc_plan_info(const qldpc_plan *plan, int what);
 
+/* Executed-work counter of a min-sum plan: check-to-variable messages actually computed by the kernel since plan creation or the
+ * last reset (a decode that converges in the middle of an iteration, decoders.py:175-176, executes fewer than E x iterations;
+ * bench.py states the roofline fraction of executed work beside the one of SURVEY's whole-iteration accounting).  Synchronises
+ * the device.  Returns -1 on error, 0 for other decoders. */
+int64_t qldpc_plan_work(qldpc_plan *plan, int reset);
+
 /* Decode `shots` syndromes.  Replaces the per-shot calls NG_decoder / BF_decoder / MS_decoder / BP_decoder
  * (decoders.py:27, :74, :110, :189 as driven by simulator.py:270-284).
  *   syn_bits  dev  [shots][qldpc_words(m)]   in   syndromes, bit-packed
@@ -140,6 +146,13 @@ int qldpc_classify(const qldpc_plan *plan_x, const qldpc_plan *plan_z,
  *   Z operators -- ker(Hx) modulo rowspace(Hz); for the plan built from Hx pass the logical X operators.  With both
  *   attached, qldpc_classify also fills QLDPC_CNT_TRUE_DEGEN / _LOGICAL (it always fills _FAIL_ANY).  k = 0 detaches. */
 int qldpc_plan_set_logicals(qldpc_plan *plan, const uint32_t *logical_rows, int32_t k);
+
+/* The shot loop of simulator.py:244-304 on HOST buffers (pinned or pageable): the bit-packed measurement record -- its four
+ * column groups [sy_z | sy_x | errX | errZ] (simulator.py:249-252) as four arrays -- in, the counters of qldpc_classify out
+ * (host int64[QLDPC_NUM_COUNTERS], overwritten).  plan_x decodes the X errors (built from Hz), plan_z the Z errors (from Hx).
+ * Host-to-device copies of one chunk overlap the decodes and the classification of the previous one; blocks until done. */
+int qldpc_simulate_host(qldpc_plan *plan_x, qldpc_plan *plan_z, const uint32_t *syn_z_bits, const uint32_t *syn_x_bits,
+                        const uint32_t *errx_bits, const uint32_t *errz_bits, int64_t shots, int64_t *counters);
 
 /* On-device depolarizing sampler + syndrome generator: the stand-in for Stim's sampler
  * (simulator.py:43-160, :196-197).  Qubit q of global shot s draws u from a counter-based generator keyed by

@@ -21,7 +21,7 @@ ABI_VERSION = 2
 # every symbol include/qldpc_b200.h declares
 EXPORTS = ["qldpc_abi_version", "qldpc_last_error", "qldpc_words", "qldpc_plan_create", "qldpc_plan_destroy",
            "qldpc_plan_info", "qldpc_decode", "qldpc_decode_host", "qldpc_osd", "qldpc_classify", "qldpc_sample",
-           "qldpc_launch_count", "qldpc_plan_set_logicals"]
+           "qldpc_launch_count", "qldpc_plan_set_logicals", "qldpc_plan_work", "qldpc_simulate_host"]
 
 
 class Graph(ctypes.Structure):
@@ -65,6 +65,9 @@ def lib():
     L.qldpc_sample.argtypes = [vp, vp, f64, u64, i64, i64, vp, vp, vp, vp, vp]
     L.qldpc_launch_count.restype = i64
     L.qldpc_plan_set_logicals.argtypes = [vp, vp, i32]
+    L.qldpc_simulate_host.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp]
+    L.qldpc_plan_work.argtypes = [vp, ctypes.c_int]
+    L.qldpc_plan_work.restype = i64
     if L.qldpc_abi_version() != ABI_VERSION:
         raise QldpcError("libqldpc_b200.so ABI version mismatch; rebuild")
     _lib = L

@@ -57,6 +57,7 @@ struct DecodeIO {
     int *fail_shot;          // [fail_cap]
     double *fail_llr;        // [fail_cap][n]
     int fail_cap;
+    unsigned long long *work_done;      // min-sum: += check-to-variable messages actually computed (one add per warp at kernel exit)
 };
 
 struct MsConst {
@@ -94,6 +95,7 @@ struct qldpc_plan {
     int logical_k = 0, lkw = 0;
     unsigned long long *d_work = nullptr;
     int *d_fail_count = nullptr;
+    unsigned long long *d_work_done = nullptr;   // executed edge updates of the min-sum kernel since creation / the last reset
     int sm_count = 0;
     int rank_h = 0;                // GF(2) rank of H
     int row_w = 0;                 // true max row weight (tab.dc may be padded to the instantiated kernel shape)

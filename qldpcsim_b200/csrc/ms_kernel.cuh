@@ -76,7 +76,7 @@ struct MsTables {
     int off_layer;       // u16 [nl][8]   16-byte record per step (a layer, or a merged run of layers): {qb, qe (range in layer_chk),
                          //               lanes per check (1, 2, 4 or 8), vb, ve (range in lvar, 32-bit entries, multiples of 32), 1 if
                          //               the second sub-group of the step's LAST pair-trip is empty (a single-variable trip is run
-                         //               instead), number of sub-layers of a merged step (0: plain layer), 0}
+                         //               instead), number of sub-layers of a merged step (0: plain layer), edges of the step}
     int off_layer_chk;   // u16 [...]     check indices, layer by layer
     int off_lvar;        // u32 [...]     lo16 = 4*j'_a, hi16 = 4*j'_b: the two variables of (trip, lane); dummy = 4*n.  With
                          //               0 < DMIN < DV the FIRST entry of a quad trip (two consecutive entries) holds variables of degree <= DMIN only
@@ -368,6 +368,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
     const float Tf = c.Tf;
     const bool init_bit = 0.0f < Tf;                    // decision of a variable whose sum is still 0 (only if L < 0)
 
+    unsigned long long edges_done = 0;                  // check-to-variable messages computed by this team (executed-work counter)
     for (;;) {
         long long shot = 0;
         if (tl == 0) {
@@ -415,7 +416,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
 
         bool converged = false;
         int it = 0;
+        uint32_t shot_edges = 0;
         if (c.max_iter > 0) {
+            shot_edges = sld_u16(layer_rec + 14u);
             // ---------------- first layer step: prior is the binary32-rounded L (decoders.py:148-149) and the variable
             // phase visits EVERY variable (the reference recomputes all posteriors; a variable outside layer 0 has
             // posterior L, which may be negative for p > 1/2)
@@ -434,6 +437,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
                 uint32_t r0, r1, r2, r3;                                       // the layer's 16-byte record
                 asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(layer_rec + 16u * l));
                 const int qb = r0 & 0xffffu, qe = r0 >> 16, lpc = r1 & 0xffffu;
+                shot_edges += r3 >> 16;
                 if (lpc == 1) ms_check_phase<DC, 1>(qb, qe, sub, W, lane, A, c.L, c.abeta, c.sgn);
                 else if (lpc == 2) ms_check_phase<DC, 2>(qb, qe, sub, W, lane, A, c.L, c.abeta, c.sgn);
                 else if (lpc == 4) ms_check_phase<DC, 4>(qb, qe, sub, W, lane, A, c.L, c.abeta, c.sgn);
@@ -548,6 +552,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
         // iterations: it+1 of decoders.py:176 on a converging break (the outer ++it has already run; a convergence in the
         // very first step leaves it == 0), else max_iter (:182)
         const int iters = (converged && it == 0) ? 1 : it;
+        edges_done += shot_edges;
         // ---- outputs: e_j = (S_j' < Tf)
         for (int w = sub; w < t.nw; w += W) {
             const int j = w * 32 + lane;
@@ -578,6 +583,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
         }
         team_sync();
     }
+    if (io.work_done && tl == 0 && edges_done) atomicAdd(io.work_done, edges_done);
 }
 
 }  // namespace qldpc

@@ -264,6 +264,8 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
     }
     CU_TRY(cudaMalloc((void **)&p->d_work, 4 * sizeof(unsigned long long)));
     CU_TRY(cudaMalloc((void **)&p->d_fail_count, 4 * sizeof(int)));
+    CU_TRY(cudaMalloc((void **)&p->d_work_done, sizeof(unsigned long long)));
+    CU_TRY(cudaMemset(p->d_work_done, 0, sizeof(unsigned long long)));
     for (int s = 0; s < 3; ++s) CU_TRY(cudaStreamCreateWithFlags(&p->streams[s], cudaStreamNonBlocking));
     for (int e = 0; e < 8; ++e) CU_TRY(cudaEventCreateWithFlags(&p->events[e], cudaEventDisableTiming));
     PlanKernels *pk = new PlanKernels();
@@ -408,6 +410,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
                 for (int x = pl.lvar_ptr[l + 1] - 32; single && x < pl.lvar_ptr[l + 1]; ++x) single = ((pl.lvar[x] >> 16) & 0xfffcu) == 4u * (uint32_t)n;
                 r[5] = single ? 1 : 0;
                 r[6] = (uint16_t)(grp[l + 1] - grp[l] > 1 ? grp[l + 1] - grp[l] : 0);
+                { int ed = 0; for (int q = step_ptr[l]; q < step_ptr[l + 1]; ++q) ed += p->row_ptr[p->layer_chk[q] + 1] - p->row_ptr[p->layer_chk[q]]; r[7] = (uint16_t)std::min(ed, 65535); }
                 if (r[6] && pl.lvar_ptr[l + 1] - pl.lvar_ptr[l] > 64 * W) return bail(QLDPC_EINVAL, "internal: merged step exceeds one quad trip per warp");
             }
             mt.off_layer_chk = put((int)p->layer_chk.size());
@@ -602,7 +605,7 @@ int qldpc_plan_destroy(qldpc_plan *p)
     if (!p) return QLDPC_OK;
     cudaSetDevice(p->device);
     cudaFree(p->d_blob); cudaFree(p->d_row_ptr); cudaFree(p->d_col_idx); cudaFree(p->d_col_ptr); cudaFree(p->d_row_idx);
-    cudaFree(p->d_hbits); cudaFree(p->d_hcol); cudaFree(p->d_lcol); cudaFree(p->d_work); cudaFree(p->d_fail_count);
+    cudaFree(p->d_hbits); cudaFree(p->d_hcol); cudaFree(p->d_lcol); cudaFree(p->d_work); cudaFree(p->d_fail_count); cudaFree(p->d_work_done);
     for (int s = 0; s < 7; ++s) if (p->scratch[s]) cudaFree(p->scratch[s]);
     delete kernels_of(p);
     for (int s = 0; s < 3; ++s) if (p->streams[s]) cudaStreamDestroy(p->streams[s]);
@@ -630,6 +633,16 @@ int qldpc_plan_set_logicals(qldpc_plan *p, const uint32_t *rows, int32_t k)
     if (rc) return rc;
     p->logical_k = k; p->lkw = kw;
     return QLDPC_OK;
+}
+
+int64_t qldpc_plan_work(qldpc_plan *p, int reset)
+{
+    if (!p) return -1;
+    if (cudaSetDevice(p->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return -1;
+    unsigned long long v = 0;
+    if (cudaMemcpy(&v, p->d_work_done, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (reset && cudaMemset(p->d_work_done, 0, sizeof(v)) != cudaSuccess) return -1;
+    return (int64_t)v;
 }
 
 int64_t qldpc_plan_info(const qldpc_plan *p, int what)
@@ -667,6 +680,7 @@ static int launch_decode(qldpc_plan *p, const uint32_t *syn, int64_t shots, uint
     io.syn = syn; io.ehat = ehat; io.iters = iters; io.conv = conv; io.llr = llr; io.shots = shots;
     io.work_counter = p->d_work + slot;
     io.fail_count = fail_count; io.fail_shot = fail_shot; io.fail_llr = fail_llr; io.fail_cap = fail_cap;
+    io.work_done = p->d_work_done;
     CU_TRY(cudaMemsetAsync(p->d_work + slot, 0, sizeof(unsigned long long), st));
     const int grid = (int)std::min<int64_t>(p->grid, (shots + p->shots_per_cta - 1) / p->shots_per_cta);
     const qldpc_opts &o = p->opts;
@@ -865,6 +879,60 @@ int qldpc_classify(const qldpc_plan *px, const qldpc_plan *pz, const uint32_t *e
 #undef QLDPC_CLS
     g_launches++;
     CU_TRY(cudaGetLastError());
+    return QLDPC_OK;
+}
+
+// The whole shot loop of simulator.py:244-304 on HOST buffers: the measurement record (bit-packed [sy_z | sy_x | errX | errZ], as
+// four arrays) in, the outcome counters out.  Chunks are double buffered on two streams of plan_x: H2D of chunk k+1 overlaps the
+// decodes and the classification of chunk k; the counters accumulate on the device and are read back once (80 bytes).
+int qldpc_simulate_host(qldpc_plan *px, qldpc_plan *pz, const uint32_t *synz, const uint32_t *synx, const uint32_t *errx,
+                        const uint32_t *errz, int64_t shots, int64_t *counters)
+{
+    if (!px || !pz || !counters || shots < 0) return fail(QLDPC_EINVAL, "null argument");
+    if (px->tab.n != pz->tab.n) return fail(QLDPC_EINVAL, "Hx and Hz must have the same number of columns (physical qubits).");
+    if (px->device != pz->device) return fail(QLDPC_EINVAL, "both plans must live on the same device");
+    if (shots && (!synz || !synx || !errx || !errz)) return fail(QLDPC_EINVAL, "null argument");
+    CU_TRY(cudaSetDevice(px->device));
+    const int nw = px->tab.nw, mzw = px->tab.mw, mxw = pz->tab.mw;
+    static const int64_t chunk_env = [] { const char *ev = getenv("QLDPC_HOST_CHUNK"); return ev ? atoll(ev) : 0ll; }();   // tuning knob
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(shots, 1), chunk_env > 0 ? chunk_env : (1 << 18)));
+    auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const size_t b_sz = al((size_t)chunk * mzw * 4), b_sx = al((size_t)chunk * mxw * 4), b_n = al((size_t)chunk * nw * 4), b_it = al((size_t)chunk * 4);
+    const size_t per_slot = b_sz + b_sx + 4 * b_n + 2 * b_it;
+    int rc;
+    if ((rc = ensure_scratch(px, 6, per_slot * 2 + 256))) return rc;
+    unsigned long long *d_cnt = (unsigned long long *)((unsigned char *)px->scratch[6] + per_slot * 2);
+    CU_TRY(cudaMemsetAsync(d_cnt, 0, QLDPC_NUM_COUNTERS * sizeof(unsigned long long), px->streams[0]));
+    CU_TRY(cudaEventRecord(px->events[0], px->streams[0]));
+    CU_TRY(cudaStreamWaitEvent(px->streams[1], px->events[0], 0));
+    const bool osd = (px->opts.osd_order >= 0 && px->opts.dec_type >= QLDPC_MS) || (pz->opts.osd_order >= 0 && pz->opts.dec_type >= QLDPC_MS);
+    int64_t k = 0;
+    for (int64_t s0 = 0; s0 < shots; s0 += chunk, ++k) {
+        const int slot = (int)(k & 1);
+        const int64_t ns = std::min(chunk, shots - s0);
+        cudaStream_t st = px->streams[slot];
+        unsigned char *base = (unsigned char *)px->scratch[6] + per_slot * slot;
+        uint32_t *d_sz = (uint32_t *)base, *d_sx = (uint32_t *)(base + b_sz);
+        uint32_t *d_ex = (uint32_t *)(base + b_sz + b_sx), *d_ez = d_ex + b_n / 4, *d_hx = d_ez + b_n / 4, *d_hz = d_hx + b_n / 4;
+        int32_t *d_ix = (int32_t *)(d_hz + b_n / 4), *d_iz = d_ix + b_it / 4;
+        CU_TRY(cudaMemcpyAsync(d_sz, synz + s0 * mzw, (size_t)ns * mzw * 4, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(d_sx, synx + s0 * mxw, (size_t)ns * mxw * 4, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(d_ex, errx + s0 * nw, (size_t)ns * nw * 4, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(d_ez, errz + s0 * nw, (size_t)ns * nw * 4, cudaMemcpyHostToDevice, st));
+        if (osd) {
+            // OSD plans share their failure scratch between chunks: one chunk at a time
+            CU_TRY(cudaStreamSynchronize(px->streams[slot ^ 1]));
+            if ((rc = qldpc_decode(px, d_sz, ns, d_hx, d_ix, nullptr, nullptr, st))) return rc;
+            if ((rc = qldpc_decode(pz, d_sx, ns, d_hz, d_iz, nullptr, nullptr, st))) return rc;
+        } else {
+            if ((rc = launch_decode(px, d_sz, ns, d_hx, d_ix, nullptr, nullptr, nullptr, nullptr, nullptr, 0, slot, st))) return rc;
+            if ((rc = launch_decode(pz, d_sx, ns, d_hz, d_iz, nullptr, nullptr, nullptr, nullptr, nullptr, 0, slot, st))) return rc;
+        }
+        if ((rc = qldpc_classify(px, pz, d_ex, d_ez, d_hx, d_hz, d_sz, d_sx, d_ix, d_iz, ns, (int64_t *)d_cnt, st))) return rc;
+    }
+    CU_TRY(cudaStreamSynchronize(px->streams[1]));
+    CU_TRY(cudaMemcpyAsync(counters, d_cnt, QLDPC_NUM_COUNTERS * sizeof(int64_t), cudaMemcpyDeviceToHost, px->streams[0]));
+    CU_TRY(cudaStreamSynchronize(px->streams[0]));
     return QLDPC_OK;
 }
 

@@ -104,6 +104,10 @@ class Decoder:
                 "steps_per_iteration", "warps_per_shot"]
         return {k: int(L.qldpc_plan_info(self._h, i)) for i, k in enumerate(keys)}
 
+    def work_done(self, reset: bool = False) -> int:
+        """Check-to-variable messages the min-sum kernel actually computed since plan creation / the last reset (synchronises)."""
+        return int(_lib.lib().qldpc_plan_work(self._h, 1 if reset else 0))
+
     # ------------------------------------------------------------------------------------------ device API
     def decode_packed(self, syn_bits, *, want_converged: bool = True, want_llr: bool = False, out=None):
         """Device tensors in / out.  syn_bits: int32 CUDA tensor (shots, words(m)).

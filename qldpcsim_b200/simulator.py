@@ -154,6 +154,18 @@ class Pipeline:
         return counters
 
 
+    def run_host(self, syn_z, syn_x, err_x, err_z, counters=None):
+        """The whole shot loop on HOST buffers (qldpc_simulate_host): bit-packed int32 host tensors / arrays of the record's four
+        column groups in, the int64[10] outcome counters out (a pinned host tensor, returned).  Copies, both decodes and the
+        classification are pipelined chunk by chunk inside the library."""
+        t = self.torch
+        if counters is None:
+            counters = t.zeros(_lib.NUM_COUNTERS, dtype=t.int64)
+        ptr = lambda a: a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+        _lib.check(_lib.lib().qldpc_simulate_host(self.decX.handle, self.decZ.handle, ptr(syn_z), ptr(syn_x), ptr(err_x), ptr(err_z),
+                                                 int(syn_z.shape[0]), ptr(counters)))
+        return counters
+
     def decode_host(self, syn_z, syn_x, out_x, out_z):
         """Host-buffer decode of both error types (qldpc_decode_host, pinned or pageable memory): syn_* are int32 host tensors
         (shots, words(m)), out_* = (ehat int32 (shots, words(n)), iters int32 (shots,), converged uint8 (shots,)).  The two

@@ -470,3 +470,23 @@ def test_osd_shared_memory_kernel_still_exact(cuda_device):
                         "test_golden_osd or (test_osd_config3_size_against_oracle and 700)"], env=env, capture_output=True, text=True, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout
+
+
+@pytest.mark.parametrize("dt,sched,osd,shots", [("MS", "L", -1, 3 * (1 << 18) + 7), ("MS", "L", 0, 6000), ("BP", "F", -1, 6000), ("NG", "F", -1, 6000)])
+def test_simulate_host_matches_device_path(dt, sched, osd, shots, cuda_device):
+    """qldpc_simulate_host (host record in, counters out; chunks double buffered on two streams) gives the counters of the
+    device-resident path (decode X, decode Z, classify) on the same batch -- several chunks in flight, OSD plans, other decoders."""
+    import torch
+    from qldpcsim_b200 import pcmlibrary, simulator
+    Hx, Hz = pcmlibrary.by_name("LP04_0")
+    pipe = simulator.Pipeline(Hx, Hz, 0.08, dt, 12, sched, osd, logicals=True)
+    batch = pipe.sample_device(shots, 3, 0)
+    want = pipe.run(*batch).cpu()
+    host = [b.cpu().contiguous() for b in batch]
+    got = pipe.run_host(*host)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want), (got.tolist(), want.tolist())
+    assert int(got[6]) == shots
+    # pageable NumPy arrays are accepted as well, and the call can be repeated on the same plans
+    got2 = pipe.run_host(*[h.numpy() for h in host])
+    assert torch.equal(got2, want)
