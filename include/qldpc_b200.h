@@ -71,7 +71,7 @@ typedef struct {
     double  beta;               /* MS normalisation (decoders.py:115), 0.75 in the driver               */
     double  eps;                /* BP clamp shift (decoders.py:195, :257-258)                           */
     int32_t osd_order;          /* OSDorder (decoders.py:116, :194); < 0 disables                       */
-    int32_t reserved;           /* min-sum: 0 automatic, 1 never merge runs of disjoint layers into one step (A/B) */
+    int32_t reserved;           /* min-sum A/B switches: bit 0 never merge runs of disjoint layers, bit 1 no 8-lane kernel */
 } qldpc_opts;
 
 typedef struct qldpc_plan qldpc_plan;

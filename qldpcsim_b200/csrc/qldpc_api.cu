@@ -12,6 +12,7 @@
 #include "hard_kernels.cuh"
 #include "ms_kernel.cuh"
 #include "ms_plan.h"
+#include "ms_sub_kernel.cuh"
 #include "osd_kernel.cuh"
 #include "sampler_kernel.cuh"
 
@@ -130,7 +131,10 @@ struct Geometry {
 }  // namespace
 
 // Extra per-plan state that needs the kernel types.
+typedef void (*ms_sub_kernel_t)(MsTables, MsSubTables, const uint16_t *, MsConst, DecodeIO);
 struct PlanKernels {
+    ms_sub_kernel_t ms_sub = nullptr;   // eight-lanes-per-shot kernel (every layer a single check, nothing to merge), or null
+    MsSubTables sub_tab{};
     ms_kernel_t ms = nullptr;
     MsTables ms_tab{};
     int ms_full_regions = 0;
@@ -332,7 +336,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
                 return mx;
             };
             static const bool merge_env = [] { const char *ev = getenv("QLDPC_MS_MERGE"); return !ev || atoi(ev) != 0; }();   // tuning knob
-            const bool can_merge = merge_env && ms_spec_available(dc_inst) && o->reserved != 1;
+            const bool can_merge = merge_env && ms_spec_available(dc_inst) && !(o->reserved & 1);
             std::vector<int> grp;                       // step -> first layer
             // Teams of two warps per shot: when the shot state allows only few shots per SM (LP118_2, Tanner: 10), one warp per
             // shot leaves the schedulers idle.  Decided on the state size (tables are ~10-35 KB), row-weight class 8 only.
@@ -359,6 +363,21 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             std::vector<int> step_ptr(nsteps + 1);       // step -> range in layer_chk
             for (int g2 = 0; g2 <= nsteps; ++g2) step_ptr[g2] = p->layer_ptr[grp[g2]];
             pk->ms_spec = spec;
+            // ---- eight lanes per shot (ms_sub_kernel.cuh): every layer is one check and nothing could be merged (bicycle)
+            bool use_sub = !spec && nl >= 1 && !(o->reserved & 2) && dc <= 32;
+            for (int l = 0; use_sub && l < nl; ++l) use_sub = p->layer_ptr[l + 1] - p->layer_ptr[l] == 1;
+            static const bool sub_env = [] { const char *ev = getenv("QLDPC_MS_SUB"); return !ev || atoi(ev) != 0; }();   // tuning knob
+            use_sub = use_sub && sub_env;
+            if (use_sub) {
+                const int dcs = std::max(8, (dc + 7) & ~7);
+                dc_inst = dcs;
+                W = 1; pk->ms_team = 1;
+                if (dcs == 24 && dv_inst == 9 && full_regions >= 9) { pk->ms_sub = ms_sub_kernel<24, 9, 9>; dmin = 9; }
+                else {
+                    dv_inst = 16; dmin = 0; full_regions = 0; pk->ms_full_regions = 0;
+                    pk->ms_sub = dcs == 8 ? ms_sub_kernel<8, 16, 0> : (dcs == 16 ? ms_sub_kernel<16, 16, 0> : (dcs == 24 ? ms_sub_kernel<24, 16, 0> : ms_sub_kernel<32, 16, 0>));
+                }
+            }
             if (spec || W == 2) {
                 int a1, a2, a3;
                 pk->ms = ms_select(dc, dv, full_regions, W == 2 ? 2 : 0, spec, &a1, &a2, &a3);
@@ -375,6 +394,45 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
                 pk->ms = ms_select(dc, dv, 0, W == 2 ? 2 : 0, spec, &a1, &a2, &dmin);
                 pl = MsPlanLayout();
                 ms_plan_layout(gv, dc_inst, dv_inst, dmin, /*search=*/true, pl, W);
+            }
+            std::vector<uint16_t> svar;                 // sub-warp kernel: variables of every layer's check in (trip, lane-in-group) order
+            if (use_sub) {
+                // The four shots of a warp are interleaved word by word, so inside a group of 8 lanes an access to variable j' falls
+                // on bank 4 (j' mod 8) + group: each trip of 8 variables -- and, with the same grouping, each slot step of the check
+                // phase -- takes variables with distinct j' mod 8 as far as the check has them (largest residue classes first).
+                const int spl = dc_inst / 8;
+                pl.slot_edge.assign((size_t)m * dc_inst, -1);
+                std::vector<std::vector<int>> cell(m);      // per check: edge of cell (trip * 8 + lane), -1 = none
+                for (int i = 0; i < m; ++i) {
+                    std::vector<std::vector<int>> by_res(8);
+                    for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x) by_res[pl.perm[p->col_idx[x]] & 7].push_back(x);
+                    cell[i].assign((size_t)spl * 8, -1);
+                    int left = p->row_ptr[i + 1] - p->row_ptr[i];
+                    for (int tr = 0; tr < spl && left > 0; ++tr) {
+                        const int need = std::min(8, std::max(0, left - 8 * (spl - tr - 1)));   // what the later trips cannot hold
+                        int taken = 0;
+                        for (int round = 0; round < 8 && (round == 0 || taken < need); ++round) {
+                            int rs[8];
+                            for (int r = 0; r < 8; ++r) rs[r] = r;
+                            std::stable_sort(rs, rs + 8, [&](int a2, int b2) { return by_res[a2].size() > by_res[b2].size(); });
+                            for (int ri = 0; ri < 8 && taken < 8; ++ri) {
+                                const int r = rs[ri];
+                                if (by_res[r].empty() || (round > 0 && taken >= need)) continue;
+                                cell[i][tr * 8 + taken] = by_res[r].back();
+                                by_res[r].pop_back();
+                                ++taken;
+                            }
+                        }
+                        left -= taken;
+                    }
+                    for (int tr = 0; tr < spl; ++tr)
+                        for (int h2 = 0; h2 < 8; ++h2) pl.slot_edge[(size_t)i * dc_inst + h2 * spl + tr] = cell[i][tr * 8 + h2];
+                }
+                for (int l = 0; l < nl; ++l) {
+                    const int i = p->layer_chk[p->layer_ptr[l]];
+                    for (int x = 0; x < spl * 8; ++x) svar.push_back((uint16_t)(4 * (cell[i][x] >= 0 ? pl.perm[p->col_idx[cell[i][x]]] : n)));
+                }
+                if (svar.size() > 65535 * 4) return bail(QLDPC_ETOOBIG, "layer list too long for the sub-warp kernel");
             }
             p->plan_wavefronts = pl.wavefronts; p->plan_wavefronts_ideal = pl.ideal;
             mt.m = m; mt.n = n; mt.E = E; mt.dc = dc_inst; mt.dv = dv; mt.nl = nsteps; mt.mw = t.mw; mt.nw = t.nw;
@@ -447,11 +505,16 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             }
             mt.off_unperm = put(32 * t.nw);
             for (int j = 0; j < 32 * t.nw; ++j) b[mt.off_unperm + j] = (uint16_t)(4 * (j < n ? pl.perm[j] : n));
+            if (use_sub) {
+                pk->sub_tab.off_svar = put((int)svar.size());
+                std::copy(svar.begin(), svar.end(), b.begin() + pk->sub_tab.off_svar);
+            }
             b.resize((b.size() + 7) & ~size_t(7), 0);
             mt.len = (int)b.size();
             t.len = mt.len;
             state = ms_layout(mt).bytes;
             fn = (const void *)pk->ms;
+            if (use_sub) { state *= 4; fn = (const void *)pk->ms_sub; }      // a warp holds four interleaved shots
         } else {
             // ================= sum-product tables (slot-major edge layout, see common.cuh) =================
             // Slot stride of the binary64 c2v array.  lane = (check of the pass, slot): a stride of 4 (mod 16) puts the slots of the
@@ -550,18 +613,20 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             return bail(QLDPC_ETOOBIG, "decoder state of one shot does not fit in 227 KB of shared memory");
         const int warps_fit = (int)std::min<size_t>(64, ((size_t)kMaxSmemPerCta - blob_bytes) / state);
         int warps = std::min(warps_fit, is_ms ? kMsWarps : 32);
-        if (is_ms && pk->ms_team == 1 && !pk->ms_spec && warps_fit > kMsWarps && pk->ms_tab.dc <= 8) {           // small shot state: the 32-warp instance
+        if (is_ms && pk->ms_team == 1 && !pk->ms_spec && !pk->ms_sub && warps_fit > kMsWarps && pk->ms_tab.dc <= 8) {           // small shot state: the 32-warp instance
             int a1, a2, a3;
             pk->ms = ms_select(dc, dv, pk->ms_full_regions, 1, false, &a1, &a2, &a3);
             fn = (const void *)pk->ms;
             warps = std::min(warps_fit, kMsWarpsBig);
         }
+        const bool sub_k = is_ms && pk->ms_sub != nullptr;
+        if (sub_k) warps = std::min(warps_fit, kMsSubWarps);
         const int team = is_ms ? pk->ms_team : pk->bp_team;
         if (is_ms && team > 1) warps = std::min(warps, std::min(kMsWarps / team, 15));          // shots per CTA (named barriers 1..15)
         if (!is_ms) warps = std::min(warps, std::min(32 / team, team > 1 ? 15 : 32));        // shots per CTA (named barriers 1..15)
         p->state_bytes = state;
         p->threads = warps * team * kWarp;
-        p->shots_per_cta = warps;
+        p->shots_per_cta = sub_k ? 4 * warps : warps;
         p->smem_bytes = blob_bytes + (size_t)warps * state;
         p->grid = p->sm_count;
         CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta));   // per function, shared by all plans
@@ -694,7 +759,8 @@ static int launch_decode(qldpc_plan *p, const uint32_t *syn, int64_t shots, uint
             if ((double)f < T) f = std::nextafterf(f, INFINITY);
             c.Tf = f;
         }
-        kernels_of(p)->ms<<<grid, p->threads, p->smem_bytes, st>>>(kernels_of(p)->ms_tab, p->d_blob, c, io);
+        if (kernels_of(p)->ms_sub) kernels_of(p)->ms_sub<<<grid, p->threads, p->smem_bytes, st>>>(kernels_of(p)->ms_tab, kernels_of(p)->sub_tab, p->d_blob, c, io);
+        else kernels_of(p)->ms<<<grid, p->threads, p->smem_bytes, st>>>(kernels_of(p)->ms_tab, p->d_blob, c, io);
         break;
     }
     case QLDPC_BP: {

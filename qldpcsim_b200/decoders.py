@@ -48,8 +48,8 @@ class Decoder:
     def __init__(self, H, decType: str, *, p: Optional[float] = None, max_iter: int = 50,
                  layers: Optional[Sequence[np.ndarray]] = None, beta: float = 0.75, OSDorder: int = -1,
                  eps: float = 1e-9, device: Optional[int] = None, kernel: str = "auto"):
-        """kernel (MS only): 'auto' | 'plain' (never merge runs of layers with disjoint variable sets into one step of the
-        kernel; for A/B measurements -- results are identical)."""
+        """kernel (MS only): 'auto' | 'plain' (warp per shot and layer per step: never merge runs of layers with disjoint
+        variable sets into one step, never use the eight-lanes-per-shot kernel; for A/B measurements -- results are identical)."""
         if decType not in _lib.DEC_TYPES:
             raise ValueError("Unrecognized decoder type.")
         self.pcm: CompiledPCM = H if isinstance(H, CompiledPCM) else compile_pcm(H, find_qc=False)
@@ -77,7 +77,7 @@ class Decoder:
                        n_layers=len(lptr) - 1 if iterative else 0, layer_ptr=lptr.ctypes.data, layer_chk=lidx.ctypes.data)
         self.prior = prior_llr(p, eps) if iterative else 0.0
         o = _lib.Opts(dec_type=_lib.DEC_TYPES[decType], max_iter=self.max_iter, prior_llr=self.prior, beta=float(beta),
-                      eps=float(eps), osd_order=self.OSDorder, reserved={"auto": 0, "plain": 1}[kernel])
+                      eps=float(eps), osd_order=self.OSDorder, reserved={"auto": 0, "plain": 3}[kernel])
         self._h = ctypes.c_void_p()
         _lib.check(_lib.lib().qldpc_plan_create(ctypes.byref(g), ctypes.byref(o), self.device, ctypes.byref(self._h)))
 
