@@ -18,11 +18,11 @@ ONLY="$*"
 cap ms_headline   ms_decode  2 --code LP118_0 --dec MS --sched L --p 0.05 --shots 1000000
 cap ms_team       ms_decode  2 --code LP118_2 --dec MS --sched L --p 0.05 --shots 200000
 cap ms_serial     ms_decode  2 --code LP118_2 --dec MS --sched S --p 0.05 --shots 200000
-cap ms_bicycle    ms_decode  2 --code bicycle --dec MS --sched L --p 0.03 --shots 200000
+cap ms_bicycle    ms_sub     2 --code bicycle --dec MS --sched L --p 0.03 --shots 200000
 cap ms_flooding   ms_decode  2 --code LP118_0 --dec MS --sched F --p 0.05 --shots 200000
 cap bp            bp_decode  2 --code LP118_0 --dec BP --sched F --p 0.05 --iters 100 --shots 50000
-cap osd1          osd_kernel 2 --code LP118_0 --dec MS --sched L --p 0.10 --osd 0 --shots 50000
-cap osd2          osd_kernel 2 --code LP118_2 --dec MS --sched S --p 0.05 --osd 10 --shots 100000
+cap osd1          osd_       2 --code LP118_0 --dec MS --sched L --p 0.10 --osd 0 --shots 50000
+cap osd2          osd_       2 --code LP118_2 --dec MS --sched S --p 0.05 --osd 10 --shots 100000
 cap bf            bf_sparse  2 --code LP118_0 --dec BF --p 0.02 --shots 100000
 cap ng            ng_decode  2 --code LP118_0 --dec NG --p 0.02 --shots 100000
 cap classify      classify   1 --code LP118_0 --dec MS --sched L --p 0.05 --shots 1000000

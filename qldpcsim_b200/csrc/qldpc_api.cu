@@ -621,6 +621,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
         }
         const bool sub_k = is_ms && pk->ms_sub != nullptr;
         if (sub_k) warps = std::min(warps_fit, kMsSubWarps);
+        if (const char *ev = getenv("QLDPC_SHOTS_CAP")) { const int cap = atoi(ev); if (cap > 0) warps = std::min(warps, cap); }   // measuring knob: resident shots per CTA
         const int team = is_ms ? pk->ms_team : pk->bp_team;
         if (is_ms && team > 1) warps = std::min(warps, std::min(kMsWarps / team, 15));          // shots per CTA (named barriers 1..15)
         if (!is_ms) warps = std::min(warps, std::min(32 / team, team > 1 ? 15 : 32));        // shots per CTA (named barriers 1..15)

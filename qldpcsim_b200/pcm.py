@@ -4,15 +4,20 @@ PCM compiler (host side): dense parity-check matrix -> what the CUDA library's p
  * `load_matrix`     : the reference's input format (simulator.py:20-35): .npy or whitespace text, reduced
                        mod 2, int8.
  * `compile_pcm`     : CSR edge list in np.where(H) order (ascending check, then ascending variable --
-                       decoders.py:224), CSC, degree statistics, quasi-cyclic structure if present.
+                       decoders.py:224), CSC, degree statistics.
  * `layerize`        : the check partition of the layered / serial schedules (simulator.py:212-224).
  * `schedule_layers` : (layersX, layersZ) as the driver builds them (simulator.py:228-236).
  * `logical_operators`: bases of the logical X / Z operators of the CSS code (what the true outcome classes of
                        README.md:15-22 need; the reference never computes them).
- * `detect_qc`       : recovers (L, base shift matrix) of a circulant-permutation lifted matrix
-                       (PCMlibrary.py:129-138, 195-201) so kernels may replace index loads by arithmetic.
-The device-side tables (message layout, check-slot assignment, per-layer variable groups) are derived from the CSR + layers by
-qldpc_plan_create in csrc/ (see include/qldpc_b200.h).
+The device-side tables (message layout, check-slot assignment, per-layer variable groups, runs of layers with disjoint
+variable sets merged into one step) are derived from the CSR + layers by qldpc_plan_create in csrc/ (see include/qldpc_b200.h).
+
+Quasi-cyclic structure (PCMlibrary.py:129-138, 195-201) is exploited STRUCTURALLY by the plan builder -- the stable
+descending-degree renumbering keeps circulant blocks contiguous (bank-conflict-free lane groups), and the single-check layers of
+a circulant block row are what the merged steps of the serial schedule collapse (450 -> 16 steps on LP118_2) -- but NOT by
+computing edge addresses from (block, shift) on the device: DESIGN.md section 9 records why that trade loses (it adds integer
+instructions to an issue-bound kernel and frees too little shared memory for one more resident shot on any code of the library).
+A circulant detector that existed for that purpose was removed; `pcmlibrary.qc_base` still exposes (Bx, Bz, L) of the generators.
 """
 from __future__ import annotations
 
@@ -38,12 +43,6 @@ def load_matrix(path: str) -> np.ndarray:
 
 
 @dataclass
-class QCInfo:
-    L: int
-    base: np.ndarray        # (m/L, n/L) int32 shifts in [0, L), -1 = zero block
-
-
-@dataclass
 class CompiledPCM:
     H: np.ndarray           # int8 dense 0/1
     m: int
@@ -55,39 +54,11 @@ class CompiledPCM:
     row_idx: np.ndarray     # int32 (nnz)   CSC, ascending check per variable
     row_weight_max: int
     col_weight_max: int
-    qc: Optional[QCInfo] = None
     _cache: dict = field(default_factory=dict, repr=False)
 
 
-def detect_qc(H: np.ndarray, candidates: Optional[Sequence[int]] = None) -> Optional[QCInfo]:
-    """Largest L > 1 for which every L x L block of H is zero or a cyclic shift of the identity."""
-    H = np.asarray(H)
-    m, n = H.shape
-    if candidates is None:
-        g = int(np.gcd(m, n))
-        candidates = [L for L in range(g, 1, -1) if g % L == 0]
-    for L in candidates:
-        if L <= 1 or m % L or n % L:
-            continue
-        mb, nb = m // L, n // L
-        blocks = H.reshape(mb, L, nb, L).transpose(0, 2, 1, 3)        # (mb, nb, L, L)
-        first = blocks[:, :, 0, :]                                     # first row of each block
-        wt = first.sum(axis=-1)
-        if (wt > 1).any():
-            continue
-        shift = np.where(wt == 1, first.argmax(axis=-1), -1).astype(np.int32)
-        r = np.arange(L)
-        cols = (r[None, None, :] + np.maximum(shift, 0)[:, :, None]) % L
-        expect = np.zeros_like(blocks)
-        bi, bj = np.nonzero(shift >= 0)
-        for i, j in zip(bi, bj):
-            expect[i, j, r, cols[i, j]] = 1
-        if np.array_equal(expect, blocks):
-            return QCInfo(L=int(L), base=shift)
-    return None
-
-
-def compile_pcm(H: np.ndarray, find_qc: bool = True) -> CompiledPCM:
+def compile_pcm(H: np.ndarray, find_qc: bool = False) -> CompiledPCM:
+    """`find_qc` is accepted for compatibility and ignored (see the module docstring)."""
     H = (np.asarray(H) % 2).astype(np.int8)
     if H.ndim != 2:
         raise ValueError("parity-check matrix must be 2-D")
@@ -103,8 +74,7 @@ def compile_pcm(H: np.ndarray, find_qc: bool = True) -> CompiledPCM:
     cw = np.diff(col_ptr)
     return CompiledPCM(H=H, m=m, n=n, nnz=nnz, row_ptr=row_ptr, col_idx=var.astype(np.int32),
                        col_ptr=col_ptr, row_idx=chk[order].astype(np.int32),
-                       row_weight_max=int(rw.max(initial=0)), col_weight_max=int(cw.max(initial=0)),
-                       qc=detect_qc(H) if (find_qc and nnz) else None)
+                       row_weight_max=int(rw.max(initial=0)), col_weight_max=int(cw.max(initial=0)))
 
 
 def layerize(H: np.ndarray, serial: bool = False) -> List[np.ndarray]:

@@ -51,21 +51,6 @@ def test_compile_pcm_roundtrip(code):
         assert c.row_weight_max == H.sum(axis=1).max() and c.col_weight_max == H.sum(axis=0).max()
 
 
-def test_detect_qc():
-    for name, L in (("LP04_0", 7), ("LP118_0", 16), ("LP118_2", 30), ("T", 31)):
-        fam_idx = (name.rsplit("_", 1)[0], int(name.rsplit("_", 1)[1])) if "_" in name else (name,)
-        Bx, Bz, LL = pcmlibrary.qc_base(*fam_idx)
-        assert LL == L
-        for B, H in zip((Bx, Bz), pcmlibrary.by_name(name)):
-            q = pcm.detect_qc(H)
-            assert q is not None and q.L == L
-            assert np.array_equal(q.base, np.where(B >= 0, B % L, -1))
-            assert np.array_equal(pcmlibrary.lift(q.base, q.L), H)
-    assert pcm.detect_qc(pcmlibrary.steane_code()[0]) is None
-    # [C | C^T] of the bicycle code: weight-9 circulants, not circulant permutations
-    assert pcm.detect_qc(pcmlibrary.bicycle_code()[0]) is None
-
-
 def test_layerize_structure():
     Hx, Hz = pcmlibrary.by_name("LP118_0")
     lx, lz = pcm.schedule_layers(Hx, Hz, "L")
