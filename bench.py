@@ -116,7 +116,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
@@ -325,6 +325,7 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    clk = ClockSampler(local) if rank == 0 else None     # started before the warm-up: nvidia-smi needs ~0.5 s to deliver its first line
     for w in range(args.warmup):
         counters.zero_()
         step(w)
@@ -332,7 +333,6 @@ def run_gpu(args):
     pipe.decX.work_done(reset=True)
     pipe.decZ.work_done(reset=True)
     launches0 = lib.qldpc_launch_count()
-    clk = ClockSampler(local) if rank == 0 else None
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     per_step_counters = []
