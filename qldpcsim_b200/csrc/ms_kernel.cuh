@@ -102,6 +102,7 @@ struct MsSmemLayout {
                    // count (int32) + flip count of a merged step (int32) of a multi-warp team
     int zero_words;
     int bytes;     // multiple of 128: S_j' and every c2v word of j' sit on bank j' mod 32
+    int bytes16;   // the same rounded to 16 bytes only (ms_sub_kernel: its interleaved layout has no use for the 128-byte alignment)
 };
 
 __host__ __device__ inline MsSmemLayout ms_layout(const MsTables &t)
@@ -116,6 +117,7 @@ __host__ __device__ inline MsSmemLayout ms_layout(const MsTables &t)
     o = (o + 7) & ~7;
     l.off_team = o; o += 16;
     l.bytes = (o + 127) & ~127;
+    l.bytes16 = (o + 15) & ~15;
     return l;
 }
 

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kMsSubWarps * 32, 1) ms_sub_kernel(MsTables t,
     const MsSmemLayout lay = ms_layout(t);
     uint32_t tab;
     asm volatile("{ .reg .u64 t64; cvta.to.shared.u64 t64, %1; cvt.u32.u64 %0, t64; }" : "=r"(tab) : "l"(smem));
-    const uint32_t wbase = tab + (uint32_t)ms_table_bytes(t) + (uint32_t)warp * 4u * (uint32_t)lay.bytes;   // four interleaved shots
+    const uint32_t wbase = tab + (uint32_t)ms_table_bytes(t) + (uint32_t)warp * 4u * (uint32_t)lay.bytes16;   // four interleaved shots
     const uint32_t sbase = wbase + 4u * (uint32_t)grp;                                                      // my group's shot
     // byte offset `off` of the single-shot layout -> address in the interleaved layout
     auto at = [&](uint32_t base, uint32_t off) { return base + (off << 2); };

@@ -514,7 +514,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             t.len = mt.len;
             state = ms_layout(mt).bytes;
             fn = (const void *)pk->ms;
-            if (use_sub) { state *= 4; fn = (const void *)pk->ms_sub; }      // a warp holds four interleaved shots
+            if (use_sub) { state = 4 * (size_t)ms_layout(mt).bytes16; fn = (const void *)pk->ms_sub; }      // a warp holds four interleaved shots
         } else {
             // ================= sum-product tables (slot-major edge layout, see common.cuh) =================
             // Slot stride of the binary64 c2v array.  lane = (check of the pass, slot): a stride of 4 (mod 16) puts the slots of the
