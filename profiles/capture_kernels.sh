@@ -30,6 +30,7 @@ cap sample        sample_kernel 0 --code LP118_0 --dec MS --sched L --p 0.05 --s
 python profiles/summarize_kernels.py $O/ksum > $O/summarize_kernels.log 2>&1
 for t in ms_headline ms_serial ms_bicycle bp osd2; do
     [ -f $O/k_$t.ncu-rep ] && python profiles/ncu_lines.py $O/k_$t.ncu-rep 40 > $O/ksum/${t}_source_lines.txt 2>/dev/null
+    [ -f $O/k_$t.ncu-rep ] && python profiles/ncu_sass.py $O/k_$t.ncu-rep 0.2 > $O/ksum/${t}_sass.txt 2>/dev/null
 done
 [ -f $O/k_ms_headline.ncu-rep ] && ncu -i $O/k_ms_headline.ncu-rep --page raw --csv > $O/ksum/ms_headline_raw.csv 2>/dev/null
 rm -f $O/k_*.ncu-rep

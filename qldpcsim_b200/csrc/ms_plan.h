@@ -13,6 +13,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 namespace qldpc {
@@ -39,6 +40,9 @@ struct MsPlanLayout {
     long long wavefronts = 0, ideal = 0;   // per full iteration over all layers (check phase: S load + c2v load + c2v store;
                                            // variable phase: S load + S store + dv_inst c2v loads per sub-group)
     int search_evals = 0;
+    // eight-lane kernel (ms_sub_kernel.cuh) only: CSR edge of cell (trip, lane-in-group) of every check, -1 = none
+    int sub_spl = 0;
+    std::vector<int> sub_cell;             // [m][sub_spl * 8]
 };
 
 namespace msplan {
@@ -261,9 +265,118 @@ struct Evaluator {
 
 }  // namespace msplan
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Eight-lane kernel (ms_sub_kernel.cuh): the four shots of a warp are interleaved word by word, so inside a group of 8 lanes an
+// access to variable j' falls on bank 4 (j' mod 8) + group.  Lane h of a group handles cell (s, h) of the layer's check in step s
+// of the check phase AND the same edge's variable in trip s of the variable phase, so one assignment of the check's edges to
+// spl x 8 cells decides the conflicts of both phases: a step is conflict-free when its 8 variables are distinct mod 8, which a
+// check allows when no residue class holds more than spl of its variables.
+namespace msplan {
+
+// modelled cost of check i: 64 * (wavefronts of one access kind = max(spl, largest residue class)) + excess members (guides the
+// search towards feasibility)
+inline int sub8_check_cost(const MsGraphView &g, const std::vector<int> &perm, int i, int spl)
+{
+    int cnt[8] = {0}, mx = 0, over = 0;
+    for (int x = g.row_ptr[i]; x < g.row_ptr[i + 1]; ++x) cnt[perm[g.col_idx[x]] & 7]++;
+    for (int r = 0; r < 8; ++r) { mx = std::max(mx, cnt[r]); over += std::max(0, cnt[r] - spl); }
+    return 64 * std::max(spl, mx) + over;
+}
+
+// Renumbering search: swaps of two variables of the same degree class whose j' differ mod 8 (simulated annealing with a fixed
+// seed, bounded, stops at the conflict-free bound).  Only the checks that are layers of their own matter, i.e. all of them.
+inline int sub8_search(const MsGraphView &g, MsPlanLayout &L, int spl, const std::vector<int> &deg, int max_moves)
+{
+    const int n = g.n, m = g.m;
+    if (n < 16) return 0;
+    long long cur = 0;
+    for (int i = 0; i < m; ++i) cur += sub8_check_cost(g, L.perm, i, spl);
+    const long long bound = 64ll * spl * m;
+    uint64_t rng = 0x9E3779B97F4A7C15ull;
+    auto next = [&]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(rng >> 33); };
+    double T = 20.0;
+    int accepted = 0;
+    std::vector<int> touched;
+    std::vector<char> mark(m, 0);
+    for (int mv = 0; mv < max_moves && cur > bound; ++mv) {
+        const int a = (int)(next() % (uint32_t)n), b = (int)(next() % (uint32_t)n);      // positions j'
+        T = std::max(0.5, T * 0.99995);
+        if (((a ^ b) & 7) == 0) continue;
+        const int ja = L.order[a], jb = L.order[b];
+        if (deg[ja] != deg[jb]) continue;
+        touched.clear();
+        for (int j : {ja, jb})
+            for (int x = g.col_ptr[j]; x < g.col_ptr[j + 1]; ++x)
+                if (!mark[g.row_idx[x]]) { mark[g.row_idx[x]] = 1; touched.push_back(g.row_idx[x]); }
+        long long before = 0, after = 0;
+        for (int i : touched) before += sub8_check_cost(g, L.perm, i, spl);
+        std::swap(L.order[a], L.order[b]);
+        L.perm[ja] = b; L.perm[jb] = a;
+        for (int i : touched) { after += sub8_check_cost(g, L.perm, i, spl); mark[i] = 0; }
+        const long long d = after - before;
+        bool keep = d <= 0;
+        if (!keep) {      // exp(-d / T) against a uniform number, in integers: accept with probability 2^(-d / (T ln 2))
+            const double pr = std::exp(-(double)d / T);
+            keep = (double)(next() & 0xFFFFFF) < pr * 16777216.0;
+        }
+        if (keep) { cur += d; ++accepted; }
+        else { std::swap(L.order[a], L.order[b]); L.perm[ja] = a; L.perm[jb] = b; }
+    }
+    return accepted;
+}
+
+// Deals the edges of every check to spl trips of 8 cells: each trip takes one variable of every residue class that still has some
+// (largest classes first); only what the later trips could not hold is added as second, third ... members.  Fills L.sub_cell,
+// L.slot_edge (slot h * spl + s of the check table = cell (s, h)) and the modelled wavefronts (four access kinds per step in the
+// check phase -- S load, c2v load, c2v store -- and 1 + dv_inst in the variable phase, as in Evaluator).
+inline void sub8_deal(const MsGraphView &g, MsPlanLayout &L, int spl)
+{
+    const int m = g.m, dcs = spl * 8;
+    L.sub_spl = spl;
+    L.sub_cell.assign((size_t)m * dcs, -1);
+    L.slot_edge.assign((size_t)m * dcs, -1);
+    long long wf = 0;
+    for (int i = 0; i < m; ++i) {
+        std::vector<std::vector<int>> by_res(8);
+        for (int x = g.row_ptr[i]; x < g.row_ptr[i + 1]; ++x) by_res[L.perm[g.col_idx[x]] & 7].push_back(x);
+        int *cell = &L.sub_cell[(size_t)i * dcs];
+        int left = g.row_ptr[i + 1] - g.row_ptr[i];
+        for (int tr = 0; tr < spl; ++tr) {
+            const int need = std::min(8, std::max(0, left - 8 * (spl - tr - 1)));   // what the later trips cannot hold
+            int taken = 0, mult[8] = {0};
+            for (int round = 0; round < 8 && left > 0 && (round == 0 || taken < need); ++round) {
+                int rs[8];
+                for (int r = 0; r < 8; ++r) rs[r] = r;
+                std::stable_sort(rs, rs + 8, [&](int a2, int b2) { return by_res[a2].size() > by_res[b2].size(); });
+                for (int ri = 0; ri < 8 && taken < 8; ++ri) {
+                    const int r = rs[ri];
+                    if (by_res[r].empty() || (round > 0 && taken >= need)) continue;
+                    cell[tr * 8 + taken] = by_res[r].back();
+                    by_res[r].pop_back();
+                    mult[r]++;
+                    ++taken;
+                }
+            }
+            left -= taken;
+            int mx = 1;
+            for (int r = 0; r < 8; ++r) mx = std::max(mx, mult[r]);
+            wf += (long long)mx * (3 + 1 + L.dv_inst);
+        }
+        for (int tr = 0; tr < spl; ++tr)
+            for (int h = 0; h < 8; ++h) L.slot_edge[(size_t)i * dcs + h * spl + tr] = cell[tr * 8 + h];
+    }
+    L.wavefronts = wf;
+    L.ideal = (long long)m * spl * (3 + 1 + L.dv_inst);
+}
+
+}  // namespace msplan
+
 // dc_inst / dv_inst / dmin are the shape of the kernel instance (see qldpc_api.cu: ms_select); `search` enables the unit
 // order search (bounded number of evaluations).
-inline void ms_plan_layout(const MsGraphView &g, int dc_inst, int dv_inst, int dmin, bool search, MsPlanLayout &L, int team_warps = 1)
+// sub8 = true: layout for the eight-lane kernel (every layer one check; dc_inst a multiple of 8): the renumbering is searched under
+// the mod-8 model above and the cells are dealt by sub8_deal; the regions of the c2v array then only need to start on multiples
+// of 8 words.
+inline void ms_plan_layout(const MsGraphView &g, int dc_inst, int dv_inst, int dmin, bool search, MsPlanLayout &L, int team_warps = 1, bool sub8 = false)
 {
     const int n = g.n;
     L.dc_inst = dc_inst; L.dv_inst = dv_inst; L.dmin = dmin;
@@ -278,13 +391,13 @@ inline void ms_plan_layout(const MsGraphView &g, int dc_inst, int dv_inst, int d
     auto set_perm = [&]() { for (int jp = 0; jp < n; ++jp) L.perm[L.order[jp]] = jp; };
     set_perm();
     // regions: multiples of 32 words so that bank(c2v word of j') == bank(S_j') == j' mod 32; an unguarded region (x < dmin)
-    // has room for the always-zero word of the dummy variable n
+    // has room for the always-zero word of the dummy variable n.  (Eight-lane kernel: multiples of 8 words, no dummy variable.)
     int words = 0;
     for (int x = 0; x < 16; ++x) {
         L.cnt[x] = 0;
         if (x < dv) for (int j = 0; j < n; ++j) L.cnt[x] += deg[j] > x;
         L.coff[x] = words;
-        if (x < dv_inst) words += (L.cnt[x] + (x < dmin ? 1 : 0) + 31) & ~31;
+        if (x < dv_inst) words += sub8 ? ((L.cnt[x] + 7) & ~7) : ((L.cnt[x] + (x < dmin ? 1 : 0) + 31) & ~31);
     }
     L.c2v_words = words;
     L.edge_rank.assign(g.E, 0);
@@ -296,6 +409,12 @@ inline void ms_plan_layout(const MsGraphView &g, int dc_inst, int dv_inst, int d
     L.lpc.resize(g.nl);
     for (int l = 0; l < g.nl; ++l) L.lpc[l] = msplan::lanes_per_check(g.layer_ptr[l + 1] - g.layer_ptr[l], dc_inst, team_warps);
 
+    if (sub8) {
+        if (search) L.search_evals = msplan::sub8_search(g, L, dc_inst / 8, deg, 300000);
+        msplan::sub8_deal(g, L, dc_inst / 8);
+        L.lvar_ptr.assign(g.nl + 1, 0);
+        return;
+    }
     msplan::Evaluator ev(g, L);
     long long best = ev.total(false);
     L.search_evals = 1;

@@ -27,3 +27,24 @@ extern "C" int ms_plan_probe(int m, int n, int E, const int *row_ptr, const int 
     stats[5] = base.wavefronts;
     return 0;
 }
+
+// eight-lane kernel layout (every layer one check): renumbering searched under the mod-8 model, cells dealt by sub8_deal
+extern "C" int ms_plan_probe_sub8(int m, int n, int E, const int *row_ptr, const int *col_idx, int dcs, int dv_inst, int dmin, int search,
+                                  int *perm_out /*[n]*/, int *cell_out /*[m*dcs]*/, long long *stats /*[4]: wavefronts, ideal, accepted moves, baseline*/)
+{
+    std::vector<int> cw(n, 0), col_ptr(n + 1, 0), row_idx(E), fill(n, 0), layer_ptr(m + 1), layer_chk(m);
+    for (int x = 0; x < E; ++x) cw[col_idx[x]]++;
+    for (int j = 0; j < n; ++j) col_ptr[j + 1] = col_ptr[j] + cw[j];
+    for (int i = 0; i < m; ++i)
+        for (int x = row_ptr[i]; x < row_ptr[i + 1]; ++x) row_idx[col_ptr[col_idx[x]] + fill[col_idx[x]]++] = i;
+    for (int i = 0; i <= m; ++i) layer_ptr[i] = i;
+    for (int i = 0; i < m; ++i) layer_chk[i] = i;
+    qldpc::MsGraphView g{m, n, E, row_ptr, col_idx, col_ptr.data(), row_idx.data(), m, layer_ptr.data(), layer_chk.data()};
+    qldpc::MsPlanLayout base, L;
+    qldpc::ms_plan_layout(g, dcs, dv_inst, dmin, false, base, 1, true);
+    qldpc::ms_plan_layout(g, dcs, dv_inst, dmin, search != 0, L, 1, true);
+    std::memcpy(perm_out, L.perm.data(), sizeof(int) * n);
+    std::memcpy(cell_out, L.sub_cell.data(), sizeof(int) * (size_t)m * dcs);
+    stats[0] = L.wavefronts; stats[1] = L.ideal; stats[2] = L.search_evals; stats[3] = base.wavefronts;
+    return 0;
+}

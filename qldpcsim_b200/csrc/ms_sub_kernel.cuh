@@ -16,7 +16,19 @@
 //     different groups can never collide on a bank, whatever layers they are at; inside a group the eight accesses of an
 //     instruction fall on banks 4 (w mod 8) + g;
 //   * finishing / refilling is done by the whole warp for one group at a time (32-lane ballots for the estimate words,
-//     32-lane zero fill), flips of hard decisions are handled by the whole warp for one flipped variable at a time.
+//     32-lane zero fill);
+//   * flipped hard decisions are NOT rare here: on the bicycle code at p = 0.03 half of all steps belong to the 5 % of shots
+//     that never converge and keep oscillating, and 3 of 4 warp steps see at least one flip.  Every lane therefore toggles the
+//     residual parities of its own flipped variables in parallel -- with at most four parity words per shot (MW > 0) through
+//     one precomputed parity mask per variable, XOR-ed into the shot's parity words by fire-and-forget shared-memory
+//     reductions -- and the unsatisfied-check count is then recounted by population count (no serial loop over the flipped
+//     variables, no atomics that return a value);
+//   * a step is one dependent chain (a warp has nothing else to do and an SM holds only 8 such warps), so it is kept SHORT:
+//     lane h owns cell (s, h) of the check in slot step s of the check phase AND the same edge's variable in trip s of the
+//     variable phase (ms_plan.h: sub8_deal), hence (i) one record per (layer, lane) -- the SPL packed table entries of the lane's
+//     edges -- is all a step needs, and it is fetched one step ahead; (ii) the message a lane writes in the check phase is
+//     read back only by itself, so no warp barrier separates the phases; (iii) the posterior read in the check phase is the
+//     "old" sum of the variable phase.  All loads of a phase are issued before the first dependent operation.
 // Results are bit-identical to the warp-per-shot kernel and to the reference.
 #pragma once
 #include "ms_kernel.cuh"
@@ -25,16 +37,27 @@ namespace qldpc {
 
 constexpr int kMsSubWarps = 16;          // launch bound: 512 threads, 128 registers
 
-// extra tables of the sub-warp kernel inside the same blob: off_svar u16 [nl][DCS] = 4*j' of the variables of the layer's check
-// in (trip, lane-in-group) order, dummy 4*n; the check of layer l is layer_chk[l]
+// extra table of the sub-warp kernel inside the same blob: off_srec u32 [nl][8][SPL] = the packed entries of the cells (s, h),
+// s < SPL, of the check of layer l, PRE-SCALED for the interleaved layout: lo16 = 16*j' (byte offset of S_j' from the shot's S
+// array), hi16 = 4 * (byte offset of the edge's c2v word in the single-shot c2v array); padding cell past the row: S entry n+1
+// (+inf) and the scratch word S[n+2].  The check of layer l is layer_chk[l].
 struct MsSubTables {
-    int off_svar;
+    int off_srec;
+    int off_colmask;     // u32 [n][MW] (MW = mw <= 4 instances only): bit i of the mask of j' = check i is adjacent to j'
+    int c16[kMsMaxDv];   // 16 * word offset of region x: byte offset of the region in the interleaved c2v array
 };
 
-template <int DCS, int DV, int DMIN>
+template <int SPL>
+__device__ __forceinline__ void sub_load_rec(uint32_t a, uint32_t (&e)[SPL])
+{
+#pragma unroll
+    for (int s = 0; s < SPL; ++s) e[s] = sld_u32(a + 4u * (uint32_t)s);
+}
+
+template <int DCS, int DV, int DMIN, int MW>
 __global__ void __launch_bounds__(kMsSubWarps * 32, 1) ms_sub_kernel(MsTables t, MsSubTables ts, const uint16_t *__restrict__ blob, MsConst c, DecodeIO io)
 {
-    static_assert(DCS % 8 == 0, "eight lanes per check");
+    static_assert(DCS % 8 == 0 && DCS <= 32, "eight lanes per check");
     constexpr int SPL = DCS / 8;          // slots per lane in the check phase = trips of 8 variables in the variable phase
     extern __shared__ __align__(128) unsigned char smem[];
     {
@@ -54,20 +77,27 @@ __global__ void __launch_bounds__(kMsSubWarps * 32, 1) ms_sub_kernel(MsTables t,
     const uint32_t sbase = wbase + 4u * (uint32_t)grp;                                                      // my group's shot
     // byte offset `off` of the single-shot layout -> address in the interleaved layout
     auto at = [&](uint32_t base, uint32_t off) { return base + (off << 2); };
-    const uint32_t chk = tab + 2u * t.off_chk, layer_chk = tab + 2u * t.off_layer_chk, col_chk = tab + 2u * t.off_col_chk;
-    const uint32_t rowpar = tab + 2u * t.off_rowpar, unperm = tab + 2u * t.off_unperm, svar = tab + 2u * ts.off_svar;
-    const uint32_t m4 = 4u * t.ms;
+    const uint32_t layer_chk = tab + 2u * t.off_layer_chk, col_chk = tab + 2u * t.off_col_chk;
+    const uint32_t rowpar = tab + 2u * t.off_rowpar, unperm = tab + 2u * t.off_unperm;
+    const uint32_t srec = tab + 2u * ts.off_srec + (uint32_t)h * (4u * SPL);     // my lane's record of layer 0
     const int n = t.n;
-    const uint32_t n4 = 4u * (uint32_t)n;
+    const uint32_t n4 = 4u * (uint32_t)n, n16 = 16u * (uint32_t)n;
     const uint32_t oC = (uint32_t)lay.off_c2v, oS = (uint32_t)lay.off_S, oP = (uint32_t)lay.off_par, oY = (uint32_t)lay.off_syn;
-    const float Tf = c.Tf;
+    const uint32_t cS = sbase + 4u * oS, cC = sbase + 4u * oC, cP = sbase + 4u * oP;   // my shot's S / c2v / parity arrays (interleaved addresses)
+    const uint32_t colmask = tab + 2u * ts.off_colmask;
+    float Tf = c.Tf;
+    asm volatile("" : "+f"(Tf));              // stays in a register (the compiler would re-load it from the constant bank per use)
     const bool init_bit = 0.0f < Tf;
+
     const float inf = __int_as_float(0x7f800000);
 
     // per-group state (equal in the 8 lanes of a group)
     long long shot = -1;
     int l = 0, it = 0, unsat = 0, iters_out = 0;
     bool active = false, exhausted = false, fin = false, conv_out = false;
+    uint32_t e[SPL], i = 0;                   // record and check of layer l (fetched one step ahead)
+#pragma unroll
+    for (int s = 0; s < SPL; ++s) e[s] = 0;
 
     for (;;) {
         // ---------------- groups without a running shot: write the finished shot's results, take the next shot (whole warp, one
@@ -116,14 +146,14 @@ __global__ void __launch_bounds__(kMsSubWarps * 32, 1) ms_sub_kernel(MsTables t,
                 int u = 0;
                 if (got) {
                     // initial state: c2v = 0 (decoders.py:150), S = 0, residual = syndrome (+ H.1 if the all-zero sums decide 1)
-                    for (int i = lane; i < lay.zero_words; i += 32) sst_f32(at(gb, 4u * (uint32_t)i), 0.0f);
+                    for (int k = lane; k < lay.zero_words; k += 32) sst_f32(at(gb, 4u * (uint32_t)k), 0.0f);
                     __syncwarp();
                     if (lane == 0) sst_u32(at(gb, oS + n4 + 4u), 0x7f800000u);        // S[n+1] = +inf: the padding edges
-                    for (int i = lane; i < t.mw; i += 32) {
-                        const uint32_t w = io.syn[ns * t.mw + i];
-                        const uint32_t p0 = init_bit ? (w ^ sld_u32(rowpar + 4u * i)) : w;
-                        sst_u32(at(gb, oY + 4u * i), w);
-                        sst_u32(at(gb, oP + 4u * i), p0);
+                    for (int k = lane; k < t.mw; k += 32) {
+                        const uint32_t w = io.syn[ns * t.mw + k];
+                        const uint32_t p0 = init_bit ? (w ^ sld_u32(rowpar + 4u * k)) : w;
+                        sst_u32(at(gb, oY + 4u * k), w);
+                        sst_u32(at(gb, oP + 4u * k), p0);
                         u += __popc(p0);
                     }
                     u = __reduce_add_sync(full, u);
@@ -132,6 +162,8 @@ __global__ void __launch_bounds__(kMsSubWarps * 32, 1) ms_sub_kernel(MsTables t,
                     fin = false;
                     if (got) {
                         shot = ns; l = 0; it = 0; unsat = u;
+                        sub_load_rec<SPL>(srec, e);
+                        i = sld_u16(layer_chk);
                         if (c.max_iter > 0) active = true;
                         else { fin = true; iters_out = 0; conv_out = false; }          // decoders.py:153 with max_iter = 0: no step at all
                     } else exhausted = true;
@@ -144,20 +176,31 @@ __global__ void __launch_bounds__(kMsSubWarps * 32, 1) ms_sub_kernel(MsTables t,
 
         // ---------------- one layer step of every group (its own shot, its own layer).  Groups without a shot run along on stale
         // state with every store / flip disabled, so the warp stays convergent.
-        const uint32_t i = sld_u16(layer_chk + 2u * (uint32_t)l);
         const double prior = (it == 0 && l == 0) ? c.Lf : c.L;                      // binary32-rounded prior in the very first step (:148-149)
-        {   // ---- check phase (decoders.py:156-169): lane h holds slots h*SPL .. h*SPL+SPL-1 of the check
-            const uint32_t ct = chk + (uint32_t)(h * SPL) * m4 + 4u * i;
+        int l_next = l + 1;
+        if (l_next == t.nl) l_next = 0;
+        // all loads of the check phase, then the record of the next step
+        uint32_t sa[SPL], ca[SPL];
+        float s_old[SPL], cv[SPL];
+#pragma unroll
+        for (int s = 0; s < SPL; ++s) {
+            sa[s] = cS + (e[s] & 0xffffu);
+            ca[s] = cC + (e[s] >> 16);
+            s_old[s] = sld_f32(sa[s]);
+            cv[s] = sld_f32(ca[s]);
+        }
+        const uint32_t synw = sld_u32(at(sbase, oY + 4u * (i >> 5)));
+        uint32_t e_next[SPL];
+        sub_load_rec<SPL>(srec + (uint32_t)l_next * (32u * SPL), e_next);
+        const uint32_t i_next = sld_u16(layer_chk + 2u * (uint32_t)l_next);
+        {   // ---- check phase (decoders.py:156-169): lane h holds cells (s, h), s < SPL, of the check
             float bs[SPL];
-            uint32_t ca[SPL];
             float m1 = inf, m2 = inf;
             uint32_t px = 0;
 #pragma unroll
             for (int s = 0; s < SPL; ++s) {
-                const uint32_t e = sld_u32(ct + (uint32_t)s * m4);
-                ca[s] = at(sbase, oC + (e >> 16));
-                const double post = __dadd_rn(prior, (double)sld_f32(at(sbase, oS + (e & 0xffffu))));      // :173
-                const double v = __dsub_rn(post, (double)sld_f32(ca[s]));                                  // :177
+                const double post = __dadd_rn(prior, (double)s_old[s]);                                    // :173
+                const double v = __dsub_rn(post, (double)cv[s]);                                           // :177
                 const float b = __double2float_rn(__dmul_rn(c.abeta, v));                                  // :167-168
                 bs[s] = b;
                 px ^= __float_as_uint(b);
@@ -175,7 +218,7 @@ __global__ void __launch_bounds__(kMsSubWarps * 32, 1) ms_sub_kernel(MsTables t,
             }
             const float r1 = (m1 == inf) ? 0.0f : m1;                               // inf -> 0 (:165-166, :169)
             const float r2 = (m2 == inf) ? 0.0f : m2;
-            const uint32_t synbit = (sld_u32(at(sbase, oY + 4u * (i >> 5))) >> (i & 31u)) & 1u;
+            const uint32_t synbit = (synw >> (i & 31u)) & 1u;
             const uint32_t P = (px ^ (synbit << 31) ^ c.sgn) & 0x80000000u;
             const uint32_t r1s = __float_as_uint(r1) | P, r2s = __float_as_uint(r2) | P;
             if (active) {
@@ -186,55 +229,83 @@ __global__ void __launch_bounds__(kMsSubWarps * 32, 1) ms_sub_kernel(MsTables t,
                 }
             }
         }
-        __syncwarp();
-        // ---- variable phase (decoders.py:172-174): SPL trips of 8 variables per group
-        int delta = 0;
+        // ---- variable phase (decoders.py:172-174): trip s = the variables of my cells (s, h); the only message of theirs that
+        // changed is the one I stored myself
+        float term[SPL][DV];
 #pragma unroll
-        for (int tr = 0; tr < SPL; ++tr) {
-            const uint32_t j4 = sld_u16(svar + 2u * (uint32_t)((l * SPL + tr) * 8 + h));
-            const uint32_t sa = at(sbase, oS + j4);
-            const float s_old = sld_f32(sa);
-            float term[DV];
+        for (int s = 0; s < SPL; ++s) {
+            uint32_t cj = cC + (e[s] & 0xffffu);
+            asm volatile("" : "+r"(cj));      // keep (per-lane base) + (uniform offset): one address register per variable
 #pragma unroll
-            for (int x = 0; x < DV; ++x) {
-                term[x] = sld_f32(at(sbase, oC + (uint32_t)t.coff4[x] + j4));
-                if (x >= DMIN) term[x] = ((int)j4 < t.cnt4[x]) ? term[x] : 0.0f;
-            }
-            float s = term[0];
+            for (int x = 0; x < DV; ++x) term[s][x] = sld_f32(cj + (uint32_t)ts.c16[x]);
+        }
+        bool fl[SPL], anyf = false;
 #pragma unroll
-            for (int x = 1; x < DV; ++x) s = __fadd_rn(s, term[x]);
-            if (active) sst_f32(sa, s);
-            uint32_t flips = __ballot_sync(full, active && ((s < Tf) != (s_old < Tf)));       // hard decision flipped (:173-174)
-            while (flips) {                                                        // rare; the whole warp toggles the checks of one flipped variable
-                const int src = __ffs(flips) - 1;
-                flips &= flips - 1;
-                const uint32_t jf4 = __shfl_sync(full, j4, src);
-                int d1 = 0;
-                if (lane < DV) {
-                    const uint32_t ch = sld_u16(col_chk + (jf4 >> 1) * (uint32_t)DV + 2u * (uint32_t)lane);
-                    if (ch != 0xffffu) {
-                        const uint32_t bit = 1u << (ch & 31u);
-                        const uint32_t old = satom_xor(at(wbase + 4u * (uint32_t)(src >> 3), oP + 4u * (ch >> 5)), bit);
-                        d1 = (old & bit) ? -1 : 1;
+        for (int s = 0; s < SPL; ++s) {
+            const uint32_t j16 = e[s] & 0xffffu;
+            const bool real = j16 < n16;                                            // not a padding cell
+#pragma unroll
+            for (int x = DMIN; x < DV; ++x) term[s][x] = ((int)j16 < 4 * t.cnt4[x]) ? term[s][x] : 0.0f;
+            float sum = term[s][0];
+#pragma unroll
+            for (int x = 1; x < DV; ++x) sum = __fadd_rn(sum, term[s][x]);
+            if (active && real) sst_f32(sa[s], sum);
+            fl[s] = active && real && ((sum < Tf) != (s_old[s] < Tf));             // hard decision flipped (:173-174)
+            anyf = anyf || fl[s];
+        }
+        if (__any_sync(full, anyf)) {
+            // every lane toggles the residual parities of its own flipped variables; the count of unsatisfied checks is recounted
+            if constexpr (MW > 0) {
+                uint32_t mk[MW];
+#pragma unroll
+                for (int w = 0; w < MW; ++w) mk[w] = 0;
+#pragma unroll
+                for (int s = 0; s < SPL; ++s) {
+                    const uint32_t a = colmask + ((e[s] & 0xffffu) >> 4) * (4u * MW);
+#pragma unroll
+                    for (int w = 0; w < MW; ++w) { const uint32_t v = fl[s] ? sld_u32(a + 4u * w) : 0u; mk[w] ^= v; }
+                }
+#pragma unroll
+                for (int w = 0; w < MW; ++w) if (mk[w]) sred_xor(cP + 16u * w, mk[w]);
+                __syncwarp();
+                int u = 0;
+#pragma unroll
+                for (int w = 0; w < MW; ++w) u += __popc(sld_u32(cP + 16u * w));
+                unsat = u;
+            } else {
+#pragma unroll
+                for (int s = 0; s < SPL; ++s) {
+                    if (fl[s]) {
+                        const uint32_t a = col_chk + ((e[s] & 0xffffu) >> 3) * (uint32_t)DV;
+#pragma unroll 4
+                        for (int x = 0; x < DV; ++x) {
+                            const uint32_t ch = sld_u16(a + 2u * (uint32_t)x);
+                            if (ch != 0xffffu) sred_xor(cP + 16u * (ch >> 5), 1u << (ch & 31u));
+                        }
                     }
                 }
-                d1 = __reduce_add_sync(full, d1);
-                if (grp == (src >> 3)) delta += d1;
+                __syncwarp();
+                int u = 0;
+                for (int w = h; w < t.mw; w += 8) u += __popc(sld_u32(cP + 16u * (uint32_t)w));
+#pragma unroll
+                for (int d = 1; d < 8; d <<= 1) u += __shfl_xor_sync(full, u, d);
+                unsat = u;
             }
         }
-        unsat += delta;
         __syncwarp();
         // ---- H e == syndrome ?  (decoders.py:175-176); next layer / iteration
-        if (active) {
+        {   // (groups without a shot advance along as well: their layer state is rewritten when they take a shot)
             const bool conv_now = unsat == 0;
-            int it_next = it, l_next = l + 1;
-            if (l_next == t.nl) { l_next = 0; it_next = it + 1; }
-            if (conv_now || it_next >= c.max_iter) {
+            const int it_next = l_next == 0 ? it + 1 : it;
+            if (active && (conv_now || it_next >= c.max_iter)) {
                 active = false; fin = true;
                 conv_out = conv_now;
                 iters_out = conv_now ? it + 1 : c.max_iter;                         // :176 / :182
             }
             l = l_next; it = it_next;
+#pragma unroll
+            for (int s = 0; s < SPL; ++s) e[s] = e_next[s];
+            i = i_next;
         }
     }
 }

@@ -364,18 +364,24 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             for (int g2 = 0; g2 <= nsteps; ++g2) step_ptr[g2] = p->layer_ptr[grp[g2]];
             pk->ms_spec = spec;
             // ---- eight lanes per shot (ms_sub_kernel.cuh): every layer is one check and nothing could be merged (bicycle)
+            int sub_mw = 0;      // > 0: the eight-lane instance that toggles parities through per-variable masks of sub_mw words
             bool use_sub = !spec && nl >= 1 && !(o->reserved & 2) && dc <= 32;
             for (int l = 0; use_sub && l < nl; ++l) use_sub = p->layer_ptr[l + 1] - p->layer_ptr[l] == 1;
             static const bool sub_env = [] { const char *ev = getenv("QLDPC_MS_SUB"); return !ev || atoi(ev) != 0; }();   // tuning knob
             use_sub = use_sub && sub_env;
+            if (use_sub) {      // its records hold byte offsets of the four-shot interleaved layout in 16 bits
+                const bool fast9 = ((dc + 7) & ~7) == 24 && dv_inst == 9 && full_regions >= 9 && t.mw == 3;
+                const long long words = (long long)(fast9 ? 9 : 16) * ((n + 8) & ~7) + n + 3;
+                use_sub = 16 * words <= 65535;
+            }
             if (use_sub) {
                 const int dcs = std::max(8, (dc + 7) & ~7);
                 dc_inst = dcs;
                 W = 1; pk->ms_team = 1;
-                if (dcs == 24 && dv_inst == 9 && full_regions >= 9) { pk->ms_sub = ms_sub_kernel<24, 9, 9>; dmin = 9; }
+                if (dcs == 24 && dv_inst == 9 && full_regions >= 9 && t.mw == 3) { pk->ms_sub = ms_sub_kernel<24, 9, 9, 3>; dmin = 9; sub_mw = 3; }
                 else {
                     dv_inst = 16; dmin = 0; full_regions = 0; pk->ms_full_regions = 0;
-                    pk->ms_sub = dcs == 8 ? ms_sub_kernel<8, 16, 0> : (dcs == 16 ? ms_sub_kernel<16, 16, 0> : (dcs == 24 ? ms_sub_kernel<24, 16, 0> : ms_sub_kernel<32, 16, 0>));
+                    pk->ms_sub = dcs == 8 ? ms_sub_kernel<8, 16, 0, 0> : (dcs == 16 ? ms_sub_kernel<16, 16, 0, 0> : (dcs == 24 ? ms_sub_kernel<24, 16, 0, 0> : ms_sub_kernel<32, 16, 0, 0>));
                 }
             }
             if (spec || W == 2) {
@@ -384,8 +390,8 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             }
             MsGraphView gv{m, n, E, p->row_ptr.data(), p->col_idx.data(), p->col_ptr.data(), p->row_idx.data(), nsteps, step_ptr.data(), p->layer_chk.data()};
             MsPlanLayout pl;
-            ms_plan_layout(gv, dc_inst, dv_inst, dmin, /*search=*/true, pl, W);
-            if (dmin > 0 && dmin < dv_inst && 100ll * pl.sub_total > 115ll * pl.sub_min) {
+            ms_plan_layout(gv, dc_inst, dv_inst, dmin, /*search=*/true, pl, W, /*sub8=*/use_sub);
+            if (!use_sub && dmin > 0 && dmin < dv_inst && 100ll * pl.sub_total > 115ll * pl.sub_min) {
                 // the [low, low, any, any] quad pattern of the partially guarded instances needs too many padding sub-groups on this
                 // graph (few variables of degree <= dmin): use the instance that guards every region instead
                 full_regions = 0;
@@ -394,45 +400,6 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
                 pk->ms = ms_select(dc, dv, 0, W == 2 ? 2 : 0, spec, &a1, &a2, &dmin);
                 pl = MsPlanLayout();
                 ms_plan_layout(gv, dc_inst, dv_inst, dmin, /*search=*/true, pl, W);
-            }
-            std::vector<uint16_t> svar;                 // sub-warp kernel: variables of every layer's check in (trip, lane-in-group) order
-            if (use_sub) {
-                // The four shots of a warp are interleaved word by word, so inside a group of 8 lanes an access to variable j' falls
-                // on bank 4 (j' mod 8) + group: each trip of 8 variables -- and, with the same grouping, each slot step of the check
-                // phase -- takes variables with distinct j' mod 8 as far as the check has them (largest residue classes first).
-                const int spl = dc_inst / 8;
-                pl.slot_edge.assign((size_t)m * dc_inst, -1);
-                std::vector<std::vector<int>> cell(m);      // per check: edge of cell (trip * 8 + lane), -1 = none
-                for (int i = 0; i < m; ++i) {
-                    std::vector<std::vector<int>> by_res(8);
-                    for (int x = p->row_ptr[i]; x < p->row_ptr[i + 1]; ++x) by_res[pl.perm[p->col_idx[x]] & 7].push_back(x);
-                    cell[i].assign((size_t)spl * 8, -1);
-                    int left = p->row_ptr[i + 1] - p->row_ptr[i];
-                    for (int tr = 0; tr < spl && left > 0; ++tr) {
-                        const int need = std::min(8, std::max(0, left - 8 * (spl - tr - 1)));   // what the later trips cannot hold
-                        int taken = 0;
-                        for (int round = 0; round < 8 && (round == 0 || taken < need); ++round) {
-                            int rs[8];
-                            for (int r = 0; r < 8; ++r) rs[r] = r;
-                            std::stable_sort(rs, rs + 8, [&](int a2, int b2) { return by_res[a2].size() > by_res[b2].size(); });
-                            for (int ri = 0; ri < 8 && taken < 8; ++ri) {
-                                const int r = rs[ri];
-                                if (by_res[r].empty() || (round > 0 && taken >= need)) continue;
-                                cell[i][tr * 8 + taken] = by_res[r].back();
-                                by_res[r].pop_back();
-                                ++taken;
-                            }
-                        }
-                        left -= taken;
-                    }
-                    for (int tr = 0; tr < spl; ++tr)
-                        for (int h2 = 0; h2 < 8; ++h2) pl.slot_edge[(size_t)i * dc_inst + h2 * spl + tr] = cell[i][tr * 8 + h2];
-                }
-                for (int l = 0; l < nl; ++l) {
-                    const int i = p->layer_chk[p->layer_ptr[l]];
-                    for (int x = 0; x < spl * 8; ++x) svar.push_back((uint16_t)(4 * (cell[i][x] >= 0 ? pl.perm[p->col_idx[cell[i][x]]] : n)));
-                }
-                if (svar.size() > 65535 * 4) return bail(QLDPC_ETOOBIG, "layer list too long for the sub-warp kernel");
             }
             p->plan_wavefronts = pl.wavefronts; p->plan_wavefronts_ideal = pl.ideal;
             mt.m = m; mt.n = n; mt.E = E; mt.dc = dc_inst; mt.dv = dv; mt.nl = nsteps; mt.mw = t.mw; mt.nw = t.nw;
@@ -446,21 +413,45 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             int ms = m;
             while (ms % 8 != 4) ++ms;
             mt.ms = ms;
-            mt.off_chk = put32(dc_inst * ms);
             // padding edge: S entry n+1 (+inf) and the scratch word S[n+2], addressed relative to the c2v array like every c2v word
             const uint32_t pad_edge = (uint32_t)(4 * (n + 1)) | ((uint32_t)(4 * mt.c2v_words + 4 * (n + 2)) << 16);
-            for (int x = 0; x < dc_inst * ms; ++x) set32(mt.off_chk, x, pad_edge);
-            for (int i = 0; i < m; ++i)
-                for (int k = 0; k < dc_inst; ++k) {
-                    const int e = pl.slot_edge[(size_t)i * dc_inst + k];
-                    if (e < 0) continue;
-                    const int jp = pl.perm[p->col_idx[e]];
-                    set32(mt.off_chk, k * ms + i, (uint32_t)(4 * jp) | ((uint32_t)(mt.coff4[pl.edge_rank[e]] + 4 * jp) << 16));
+            auto chk_entry = [&](int e) {
+                if (e < 0) return pad_edge;
+                const int jp = pl.perm[p->col_idx[e]];
+                return (uint32_t)(4 * jp) | ((uint32_t)(mt.coff4[pl.edge_rank[e]] + 4 * jp) << 16);
+            };
+            if (use_sub) {
+                // the eight-lane kernel reads one record per (layer, lane) instead of the check table, the step records and the
+                // variable lists (ms_sub_kernel.cuh)
+                mt.off_chk = put32(0);
+                const int spl = dc_inst / 8;
+                const uint32_t pad16 = (uint32_t)(16 * (n + 1)) | ((uint32_t)(16 * mt.c2v_words + 16 * (n + 2)) << 16);
+                pk->sub_tab.off_srec = put32(nl * 8 * spl);
+                for (int x = 0; x < kMsMaxDv; ++x) pk->sub_tab.c16[x] = 4 * mt.coff4[x];
+                for (int l = 0; l < nl; ++l) {
+                    const int i = p->layer_chk[p->layer_ptr[l]];
+                    for (int h2 = 0; h2 < 8; ++h2)
+                        for (int s2 = 0; s2 < spl; ++s2) {
+                            const int e = pl.sub_cell[(size_t)i * dc_inst + s2 * 8 + h2];
+                            uint32_t v = pad16;
+                            if (e >= 0) {
+                                const int jp = pl.perm[p->col_idx[e]];
+                                v = (uint32_t)(16 * jp) | ((uint32_t)(4 * (mt.coff4[pl.edge_rank[e]] + 4 * jp)) << 16);
+                            }
+                            set32(pk->sub_tab.off_srec, (l * 8 + h2) * spl + s2, v);
+                        }
                 }
+                pl.lvar.clear();
+            } else {
+                mt.off_chk = put32(dc_inst * ms);
+                for (int x = 0; x < dc_inst * ms; ++x) set32(mt.off_chk, x, pad_edge);
+                for (int i = 0; i < m; ++i)
+                    for (int k = 0; k < dc_inst; ++k) set32(mt.off_chk, k * ms + i, chk_entry(pl.slot_edge[(size_t)i * dc_inst + k]));
+            }
             if (pl.lvar.size() > 65535) return bail(QLDPC_ETOOBIG, "per-layer variable lists exceed 65535 entries");
             b.resize((b.size() + 7) & ~size_t(7), 0);              // 16-byte aligned records
-            mt.off_layer = put(8 * nsteps);
-            for (int l = 0; l < nsteps; ++l) {
+            mt.off_layer = put(use_sub ? 0 : 8 * nsteps);
+            for (int l = 0; l < nsteps && !use_sub; ++l) {
                 uint16_t *r = &b[mt.off_layer + 8 * l];
                 r[0] = (uint16_t)step_ptr[l]; r[1] = (uint16_t)step_ptr[l + 1]; r[2] = (uint16_t)pl.lpc[l];
                 r[3] = (uint16_t)pl.lvar_ptr[l]; r[4] = (uint16_t)pl.lvar_ptr[l + 1];
@@ -491,11 +482,22 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
                 }
             }
             // checks of every variable in the renumbering, fixed stride (flip handling)
-            mt.off_col_chk = put((n + 1) * dv_inst);
-            std::fill(b.begin() + mt.off_col_chk, b.begin() + mt.off_col_chk + (n + 1) * dv_inst, (uint16_t)0xFFFF);
-            for (int jp = 0; jp < n; ++jp) {
-                const int j = pl.order[jp];
-                for (int x = p->col_ptr[j]; x < p->col_ptr[j + 1]; ++x) b[mt.off_col_chk + jp * dv_inst + (x - p->col_ptr[j])] = (uint16_t)p->row_idx[x];
+            if (sub_mw > 0) {
+                mt.off_col_chk = put(0);
+                pk->sub_tab.off_colmask = put32(n * sub_mw);
+                for (int jp = 0; jp < n; ++jp) {
+                    const int j = pl.order[jp];
+                    std::vector<uint32_t> mk(sub_mw, 0u);
+                    for (int x = p->col_ptr[j]; x < p->col_ptr[j + 1]; ++x) mk[p->row_idx[x] >> 5] ^= 1u << (p->row_idx[x] & 31);
+                    for (int w2 = 0; w2 < sub_mw; ++w2) set32(pk->sub_tab.off_colmask, jp * sub_mw + w2, mk[w2]);
+                }
+            } else {
+                mt.off_col_chk = put((n + 1) * dv_inst);
+                std::fill(b.begin() + mt.off_col_chk, b.begin() + mt.off_col_chk + (n + 1) * dv_inst, (uint16_t)0xFFFF);
+                for (int jp = 0; jp < n; ++jp) {
+                    const int j = pl.order[jp];
+                    for (int x = p->col_ptr[j]; x < p->col_ptr[j + 1]; ++x) b[mt.off_col_chk + jp * dv_inst + (x - p->col_ptr[j])] = (uint16_t)p->row_idx[x];
+                }
             }
             mt.off_rowpar = put32(t.mw);
             {
@@ -505,10 +507,6 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             }
             mt.off_unperm = put(32 * t.nw);
             for (int j = 0; j < 32 * t.nw; ++j) b[mt.off_unperm + j] = (uint16_t)(4 * (j < n ? pl.perm[j] : n));
-            if (use_sub) {
-                pk->sub_tab.off_svar = put((int)svar.size());
-                std::copy(svar.begin(), svar.end(), b.begin() + pk->sub_tab.off_svar);
-            }
             b.resize((b.size() + 7) & ~size_t(7), 0);
             mt.len = (int)b.size();
             t.len = mt.len;

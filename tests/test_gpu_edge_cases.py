@@ -259,3 +259,40 @@ def test_decode_host_many_chunks_serial(cuda_device):
     torch.cuda.synchronize()
     assert np.array_equal(e_h.view(np.int32), e_dev.cpu().numpy()) and np.array_equal(it_h, it_dev.cpu().numpy())
     assert np.array_equal(cv_h, cv_dev.cpu().numpy())
+
+
+@pytest.mark.parametrize("m,n,rw,cwmax", [(50, 60, 7, 16), (100, 120, 14, 16), (73, 146, 18, 9), (30, 64, 30, 16), (140, 80, 8, 16)])
+def test_ms_single_overlapping_check_layers(m, n, rw, cwmax, cuda_device):
+    """Schedules whose every layer is one check that overlaps its neighbours run on the eight-lane kernel (ms_sub_kernel.cuh):
+    every row-weight class (8 / 16 / 24 / 32 cells), one to five parity words, shots that never converge and keep flipping
+    (the flip path: per-variable parity masks with the three-word instance, check lists otherwise) -- estimates, iteration
+    counts, convergence flags and the float64 posterior of every shot against the oracle."""
+    from oracle import oracle
+    from qldpcsim_b200.decoders import Decoder
+    rng = np.random.default_rng(1000 * m + rw)
+    H = np.zeros((m, n), np.int8)
+    if (m, n, rw) == (73, 146, 18):       # the shape of the bicycle code (regular: row weight 18, column weight 9) with a random graph
+        for blk in range(2):
+            first = rng.choice(73, 9, replace=False)
+            for i in range(73):
+                H[i, 73 * blk + (first + i) % 73] = 1
+    else:
+        colw = np.zeros(n, int)
+        for i in range(m):
+            ok = np.nonzero(colw < cwmax)[0]
+            w = min(rw if i % 3 else max(1, rw - 2), len(ok))
+            idx = rng.choice(ok, w, replace=False)
+            H[i, idx] = 1
+            colw[idx] += 1
+    layers = [np.array([i]) for i in rng.permutation(m)]
+    e = (rng.random((600, n)) < 0.07).astype(np.int64)
+    syn = ((e @ H.T.astype(np.int64)) % 2).astype(np.uint8)
+    syn[:40] = rng.integers(0, 2, size=(40, m))          # mostly undecodable: oscillating decisions until the iteration limit
+    want = oracle.Graph(H).decode("MS", syn, p=0.03, max_iter=12, layers=layers, want_posterior=True)
+    dec = Decoder(H, "MS", p=0.03, max_iter=12, layers=layers)
+    got = dec.decode(syn, want_llr=True)
+    assert dec.info()["shots_per_cta"] % 4 == 0 and dec.info()["steps_per_iteration"] == m
+    assert not want["converged"].all() and want["converged"].any()
+    assert np.array_equal(got["e_hat"], want["e_hat"]) and np.array_equal(got["iters"], want["iters"])
+    assert np.array_equal(got["converged"], want["converged"])
+    assert np.array_equal(got["posterior"], want["posterior"])
