@@ -28,7 +28,7 @@ cap ng            ng_decode  2 --code LP118_0 --dec NG --p 0.02 --shots 100000
 cap classify      classify   1 --code LP118_0 --dec MS --sched L --p 0.05 --shots 1000000
 cap sample        sample_kernel 0 --code LP118_0 --dec MS --sched L --p 0.05 --shots 1000000
 python profiles/summarize_kernels.py $O/ksum > $O/summarize_kernels.log 2>&1
-for t in ms_headline ms_serial ms_bicycle bp osd2; do
+for t in ms_headline ms_team ms_serial ms_bicycle bp osd2; do
     [ -f $O/k_$t.ncu-rep ] && python profiles/ncu_lines.py $O/k_$t.ncu-rep 40 > $O/ksum/${t}_source_lines.txt 2>/dev/null
     [ -f $O/k_$t.ncu-rep ] && python profiles/ncu_sass.py $O/k_$t.ncu-rep 0.2 > $O/ksum/${t}_sass.txt 2>/dev/null
 done

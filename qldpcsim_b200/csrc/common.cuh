@@ -107,7 +107,7 @@ struct qldpc_plan {
     void *scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t events[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t events[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     void *pinned[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t pinned_bytes[4] = {0, 0, 0, 0};
 };
