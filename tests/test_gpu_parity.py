@@ -472,9 +472,9 @@ def test_osd_shared_memory_kernel_still_exact(cuda_device):
     assert " passed" in r.stdout
 
 
-@pytest.mark.parametrize("dt,sched,osd,shots", [("MS", "L", -1, 3 * (1 << 18) + 7), ("MS", "L", 0, 6000), ("BP", "F", -1, 6000), ("NG", "F", -1, 6000)])
+@pytest.mark.parametrize("dt,sched,osd,shots", [("MS", "L", -1, 5 * (1 << 18) + 7), ("MS", "L", 0, 6000), ("BP", "F", -1, 6000), ("NG", "F", -1, 6000)])
 def test_simulate_host_matches_device_path(dt, sched, osd, shots, cuda_device):
-    """qldpc_simulate_host (host record in, counters out; chunks double buffered on two streams) gives the counters of the
+    """qldpc_simulate_host (host record in, counters out; chunks of 2^19 shots double buffered on two compute streams behind a copy stream) gives the counters of the
     device-resident path (decode X, decode Z, classify) on the same batch -- several chunks in flight, OSD plans, other decoders."""
     import torch
     from qldpcsim_b200 import pcmlibrary, simulator
