@@ -29,10 +29,11 @@ struct BpConst {
 };
 
 struct BpSmemLayout {
-    int off_c2v;   // double [dc*m]
+    int off_c2v;   // double [dc*ms + 1]: the last word stays 0.0 (padding entries of the fixed-stride column table)
     int off_T;     // double [n + 1]
     int off_par, off_syn;
     int off_team;  // 16 bytes: shot index mailbox (int64), unsatisfied-check count (int32)
+    int off_tk;    // double [4][32]: the tanh factors of the pass a warp is working on (one row per warp of the team)
     int bytes;
 };
 
@@ -43,27 +44,36 @@ __host__ __device__ inline BpSmemLayout bp_layout(const Tables &t)
 {
     BpSmemLayout l;
     int o = 0;
-    l.off_c2v = o; o += 8 * t.dc * t.ms;
+    l.off_c2v = o; o += 8 * (t.dc * t.ms + 1);
     l.off_T = o;   o += 8 * (t.n + 1);
     l.off_par = o; o += 4 * t.mw;
     l.off_syn = o; o += 4 * t.mw;
     o = (o + 7) & ~7;
     l.off_team = o; o += 16;
+    o = (o + 15) & ~15;
+    l.off_tk = o;  o += 4 * 32 * 8;
     l.bytes = (o + 15) & ~15;
     return l;
 }
 
-// np.sum(c2v[edges of j]) with a warp-uniform trip count (dv_max); terms past the degree are skipped by predicate.
-__device__ __forceinline__ double bp_colsum(const double *c2v, const uint16_t *col_pos, int t0, int cnt, int dv_max)
+// np.sum over fewer than 8 terms is sequential from 0.0.  Columns are read through the fixed-stride table: DVF entries per
+// variable, entries past the degree point at a word that is always 0.0 (s + 0.0 == s; a sum that ends as -0.0 can only become
+// +0.0, which the following L0 + s and the sign tests cannot tell apart), so the loop is straight-line code without guards.
+template <int DVF>
+__device__ __forceinline__ double bp_colsum_fixed(const double *c2v, const uint16_t *row)
 {
-    if (dv_max < 8) {
-        double s = 0.0;
-        for (int x = 0; x < dv_max; ++x) {
-            const double term = c2v[col_pos[t0 + (x < cnt ? x : 0)]];
-            s = (x < cnt) ? __dadd_rn(s, term) : s;
-        }
-        return s;
-    }
+    double term[DVF];
+#pragma unroll
+    for (int x = 0; x < DVF; ++x) term[x] = c2v[row[x]];
+    double s = 0.0;
+#pragma unroll
+    for (int x = 0; x < DVF; ++x) s = __dadd_rn(s, term[x]);
+    return s;
+}
+
+// np.sum(c2v[edges of j]) for columns of 8 and more checks (any column weight)
+__device__ __forceinline__ double bp_colsum(const double *c2v, const uint16_t *col_pos, int t0, int cnt)
+{
     if (cnt < 8) {                                   // mixed degrees around 8: rare, lane-divergent but correct
         double s = 0.0;
         for (int x = 0; x < cnt; ++x) s = __dadd_rn(s, c2v[col_pos[t0 + x]]);
@@ -105,6 +115,7 @@ __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint
     const uint16_t *var_tab = tab + t.off_var;          // byte offsets 4*j
     const uint16_t *col_ptr = tab + t.off_col_ptr;
     const uint16_t *col_pos = tab + t.off_col_pos;
+    const uint16_t *colf = tab + t.off_colf;
     const uint16_t *col_chk = tab + t.off_col_chk;
     const uint16_t *layer_ptr = tab + t.off_layer_ptr;
     const uint16_t *layer_chk = tab + t.off_layer_chk;
@@ -126,6 +137,7 @@ __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint
     uint32_t *syn = reinterpret_cast<uint32_t *>(base + lay.off_syn);
     volatile long long *team_shot = reinterpret_cast<volatile long long *>(base + lay.off_team);
     int *team_unsat = reinterpret_cast<int *>(base + lay.off_team + 8);
+    double *tkw = reinterpret_cast<double *>(base + lay.off_tk) + 32 * sub;     // this warp's row
     const int m = t.ms, n = t.n, dc = t.dc;   // m: slot stride
     const double one_m_eps = 1.0 - c.eps;                     // `1-eps` of decoders.py:257
     const bool init_bit = c.L0 < 0.0;
@@ -142,7 +154,7 @@ __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint
         team_sync();
         const long long shot = *team_shot;
         if (shot >= io.shots) break;
-        for (int i = tl; i < dc * m; i += TT) c2v[i] = 0.0;         // :236
+        for (int i = tl; i <= dc * m; i += TT) c2v[i] = 0.0;        // :236 (and the always-zero word behind the array)
         for (int i = tl; i <= n; i += TT) T[i] = c.L0;              // v2c = L0 (:235)
         if (sub == 0) {
             int u = 0;
@@ -172,9 +184,22 @@ __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint
                     const bool valid = act && k < dc && joff != kPad;
                     double tk = 1.0;
                     if (valid) tk = npym_tanh(__dsub_rn(T[joff >> 2], c2v[pos]) / 2.0, nt);     // np.tanh(v2c/2) (:254, :256)
-                    double prod = 1.0;
-                    for (int x = 0; x < dc; ++x)                                       // np.prod: sequential (:253-254)
-                        prod = __dmul_rn(prod, __shfl_sync(full, tk, grp + x));
+                    // np.prod: sequential (:253-254), 1.0 * t0 = t0 exactly; the lanes past the row weight hold the exact factor 1.0.
+                    // The factors of a check travel through shared memory: one store and LPC/2 broadcast 128-bit loads per lane
+                    // instead of 2*LPC shuffles.
+                    tkw[lane] = tk;
+                    __syncwarp();
+                    double prod;
+                    {
+                        const double2 *row = reinterpret_cast<const double2 *>(tkw + grp);
+                        double2 f = row[0];
+                        prod = __dmul_rn(f.x, f.y);
+#pragma unroll
+                        for (int x = 1; x < LPC / 2; ++x) {
+                            f = row[x];
+                            prod = __dmul_rn(__dmul_rn(prod, f.x), f.y);
+                        }
+                    }
                     if (valid) {
                         double th2 = prod / tk;                                        // :256
                         if (fabs(th2) >= one_m_eps) {                                  // :257-258
@@ -193,8 +218,24 @@ __global__ void __launch_bounds__(1024, 1) bp_decode_kernel(Tables t, const uint
                 int delta = 0;
                 for (int q = vb + tl; q < ve; q += TT) {
                     const int j = first ? (q < n ? q : n) : lvar_idx[q];
-                    const int t0 = (j < n) ? col_ptr[j] : 0, cnt = (j < n) ? col_ptr[j + 1] - t0 : 0;
-                    const double tot = __dadd_rn(c.L0, bp_colsum(c2v, col_pos, t0, cnt, t.dv));   // :269 / :275
+                    double sum;
+                    if (t.dv < 8) {                                                   // warp-uniform
+                        const uint16_t *row = colf + j * t.dv;
+                        switch (t.dv) {
+                        case 0: sum = 0.0; break;
+                        case 1: sum = bp_colsum_fixed<1>(c2v, row); break;
+                        case 2: sum = bp_colsum_fixed<2>(c2v, row); break;
+                        case 3: sum = bp_colsum_fixed<3>(c2v, row); break;
+                        case 4: sum = bp_colsum_fixed<4>(c2v, row); break;
+                        case 5: sum = bp_colsum_fixed<5>(c2v, row); break;
+                        case 6: sum = bp_colsum_fixed<6>(c2v, row); break;
+                        default: sum = bp_colsum_fixed<7>(c2v, row); break;
+                        }
+                    } else {
+                        const int t0 = (j < n) ? col_ptr[j] : 0, cnt = (j < n) ? col_ptr[j + 1] - t0 : 0;
+                        sum = bp_colsum(c2v, col_pos, t0, cnt);
+                    }
+                    const double tot = __dadd_rn(c.L0, sum);                          // :269 / :275
                     const double t_old = T[j];
                     T[j] = tot;
                     uint32_t flips = __ballot_sync(full, (tot < 0.0) != (t_old < 0.0));           // :280

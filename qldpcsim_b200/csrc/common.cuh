@@ -33,11 +33,10 @@ struct Tables {
     int off_layer_chk;   // [layer_ptr[nl]]
     int off_lvar_ptr;    // [nl+1]
     int off_lvar_idx;    // [lvar_ptr[nl]]  sorted distinct variables adjacent to the checks of layer l
-    int off_layer_lpc;   // [nl]     lanes per check used by the min-sum check phase in layer l (1, 2, 4 or 8)
-    int off_vn;          // [n][dvs] BYTE offsets (4*(k*m+i)) of the edges of variable j, ascending check, padded with
-                         //          the offset of the always-zero slot 4*dc*m; dvs = 4, 8 or 16 (min-sum only)
+    int off_colf;        // [n+1][dv] the same positions with a fixed stride of dv entries per variable (columns of fewer than 8
+                         //          checks: sum-product column sums without pointer loads); past the degree -- and for the dummy
+                         //          variable n -- the always-zero word dc*ms of the c2v array
     int off_rowpar;      // [2*mw]   parity of the row weights as bit words (low half, high half)
-    int dvs;
     int n_pad;           // n rounded up to a multiple of 64 (first-step variable sweep, two variables per lane and trip)
     int ms;              // slot stride of the slot-major edge arrays (>= m; padded so that the lane groups of the
                          // min-sum check phase fall on disjoint shared-memory banks)

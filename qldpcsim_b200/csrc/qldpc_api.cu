@@ -540,13 +540,16 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
                     b[t.off_col_pos + x] = (uint16_t)(col_slot[x] * ms + p->row_idx[x]);
                     b[t.off_col_chk + x] = (uint16_t)p->row_idx[x];
                 }
-                t.dvs = 0;
-                t.off_vn = 0;
+                t.off_colf = put(dv < 8 ? (n + 1) * dv : 0);
+                if (dv < 8) {
+                    std::fill(b.begin() + t.off_colf, b.begin() + t.off_colf + (n + 1) * dv, (uint16_t)(dc * ms));
+                    for (int j = 0; j < n; ++j)
+                        for (int x = p->col_ptr[j]; x < p->col_ptr[j + 1]; ++x) b[t.off_colf + j * dv + (x - p->col_ptr[j])] = (uint16_t)(col_slot[x] * ms + p->row_idx[x]);
+                }
                 t.n_pad = (n + 31) & ~31;
                 t.off_rowpar = put(2 * t.mw);
                 for (int i = 0; i < m; ++i)
                     if ((p->row_ptr[i + 1] - p->row_ptr[i]) & 1) b[t.off_rowpar + 2 * (i >> 5) + ((i & 31) >> 4)] |= (uint16_t)(1u << (i & 15));
-                t.off_layer_lpc = put(nl);
                 t.off_layer_ptr = put(nl + 1);
                 for (int l = 0; l <= nl; ++l) b[t.off_layer_ptr + l] = (uint16_t)p->layer_ptr[l];
                 t.off_layer_chk = put((int)p->layer_chk.size());
