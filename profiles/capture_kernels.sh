@@ -19,6 +19,7 @@ cap ms_headline   ms_decode  2 --code LP118_0 --dec MS --sched L --p 0.05 --shot
 cap ms_team       ms_decode  2 --code LP118_2 --dec MS --sched L --p 0.05 --shots 200000
 cap ms_serial     ms_decode  2 --code LP118_2 --dec MS --sched S --p 0.05 --shots 200000
 cap ms_bicycle    ms_sub     2 --code bicycle --dec MS --sched L --p 0.03 --shots 200000
+cap ms_lp04       ms_decode  2 --code LP04_0 --dec MS --sched L --p 0.05 --shots 1000000
 cap ms_flooding   ms_decode  2 --code LP118_0 --dec MS --sched F --p 0.05 --shots 200000
 cap bp            bp_decode  2 --code LP118_0 --dec BP --sched F --p 0.05 --iters 100 --shots 50000
 cap osd1          osd_       2 --code LP118_0 --dec MS --sched L --p 0.10 --osd 0 --shots 50000
@@ -28,7 +29,7 @@ cap ng            ng_decode  2 --code LP118_0 --dec NG --p 0.02 --shots 100000
 cap classify      classify   1 --code LP118_0 --dec MS --sched L --p 0.05 --shots 1000000
 cap sample        sample_kernel 0 --code LP118_0 --dec MS --sched L --p 0.05 --shots 1000000
 python profiles/summarize_kernels.py $O/ksum > $O/summarize_kernels.log 2>&1
-for t in ms_headline ms_team ms_serial ms_bicycle bp osd2; do
+for t in ms_headline ms_team ms_serial ms_bicycle ms_lp04 bp osd2; do
     [ -f $O/k_$t.ncu-rep ] && python profiles/ncu_lines.py $O/k_$t.ncu-rep 40 > $O/ksum/${t}_source_lines.txt 2>/dev/null
     [ -f $O/k_$t.ncu-rep ] && python profiles/ncu_sass.py $O/k_$t.ncu-rep 0.2 > $O/ksum/${t}_sass.txt 2>/dev/null
 done

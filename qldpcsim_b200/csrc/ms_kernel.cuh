@@ -70,7 +70,7 @@ struct MsTables {
     int mw, nw;          // words(m), words(n)
     int ms;              // row stride of chk (>= m; ms = 4 mod 8 keeps the lane groups of a split check on disjoint banks)
     int n_pad;           // n rounded up to a multiple of 64 (first-step sweep: two variables per lane and trip)
-    int c2v_words;       // words of the per-shot c2v array (multiple of 32: every region starts on bank 0)
+    int c2v_words;       // words of the per-shot c2v array (regions start on multiples of 32 words -- bank 0 -- or, packed, of 16)
     int off_chk;         // u32 [dc*ms]   lo16 = 4*j' (byte offset of S_j'), hi16 = byte offset of the edge's c2v word.  Slots past the
                          //               end of a short row hold a PADDING EDGE: S entry n+1 (always +inf) and the scratch word S[n+2]
     int off_layer;       // u16 [nl][8]   16-byte record per step (a layer, or a merged run of layers): {qb, qe (range in layer_chk),
@@ -86,6 +86,7 @@ struct MsTables {
     int off_rowpar;      // u32 [mw]      parity of the row weights as bit words
     int off_unperm;      // u16 [32*nw]   4*j' of original variable j (4*n past the end)
     int len;             // blob length in uint16 units (multiple of 8)
+    int packed;          // 1: regions rounded to 16 words and shot states 16 bytes apart (ms_plan.h: packed), 0: 32 words / 128 bytes
     int cnt4[kMsMaxDv];  // 4 * number of variables of degree > x
     int coff4[kMsMaxDv]; // byte offset of region x in the c2v array
 };
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
     const int team = warp / W, sub = warp % W;
     constexpr int TT = 32 * W;
     const int tl = sub * 32 + lane;                                       // thread index within the team
-    const uint32_t wbase = tab + (uint32_t)ms_table_bytes(t) + (uint32_t)team * (uint32_t)lay.bytes;
+    const uint32_t wbase = tab + (uint32_t)ms_table_bytes(t) + (uint32_t)team * (uint32_t)(t.packed ? lay.bytes16 : lay.bytes);
     auto team_sync = [&]() {
         if constexpr (W == 1) __syncwarp();
         else asm volatile("bar.sync %0, %1;" :: "r"(team + 1), "r"(TT) : "memory");

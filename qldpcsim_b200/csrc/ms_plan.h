@@ -87,7 +87,7 @@ struct Evaluator {
         }
         int pool[2][32], np[2] = {0, 0}, take[2] = {0, 0};
         for (int x = a; x < b; ++x) {
-            const int par = (L.perm[g.col_idx[x]] >> 4) & 1;
+            const int par = ((L.coff[L.edge_rank[x]] + L.perm[g.col_idx[x]]) >> 4) & 1;      // bank half of the edge's c2v word
             pool[par][np[par]++] = x;
         }
         int left = b - a;
@@ -117,17 +117,21 @@ struct Evaluator {
                 if (store) for (int k = 0; k < dc; ++k) L.slot_edge[(size_t)i * dc + k] = slots[(size_t)q * dc + k];
             }
             for (int s = 0; s < spl; ++s) {
-                int bank[32] = {0}, any = 0;
+                // S_j' sits on bank j' mod 32 (plus a constant), the edge's c2v word on (coff[rank] + j') mod 32: the same bank when
+                // the regions start on multiples of 32 words, a per-region rotation when they are packed
+                int bank_s[32] = {0}, bank_c[32] = {0}, any = 0;
                 for (int q = 0; q < nq; ++q)
                     for (int h = 0; h < lpc; ++h) {
                         const int k = h * spl + s;
                         if (k >= dc) continue;
                         const int e = slots[(size_t)q * dc + k];
                         if (e < 0) continue;
-                        bank[L.perm[g.col_idx[e]] & 31]++;
+                        const int jp = L.perm[g.col_idx[e]];
+                        bank_s[jp & 31]++;
+                        bank_c[(L.coff[L.edge_rank[e]] + jp) & 31]++;
                         any = 1;
                     }
-                cost += 3ll * max_mult(bank);
+                cost += max_mult(bank_s) + 2ll * max_mult(bank_c);
                 if (ideal) *ideal += 3ll * any;
             }
         }
@@ -376,7 +380,11 @@ inline void sub8_deal(const MsGraphView &g, MsPlanLayout &L, int spl)
 // sub8 = true: layout for the eight-lane kernel (every layer one check; dc_inst a multiple of 8): the renumbering is searched under
 // the mod-8 model above and the cells are dealt by sub8_deal; the regions of the c2v array then only need to start on multiples
 // of 8 words.
-inline void ms_plan_layout(const MsGraphView &g, int dc_inst, int dv_inst, int dmin, bool search, MsPlanLayout &L, int team_warps = 1, bool sub8 = false)
+// packed = true: the regions of the c2v array follow each other without rounding to 32 words (the planner's bank model accounts
+// for the rotation); saves up to 31 words per region -- on LP118_0 (n = 544 = 17 * 32, so the dummy variable's word costs a
+// whole row in each of the three unguarded regions) 496 bytes per shot, which is the 21st resident shot per SM.
+inline void ms_plan_layout(const MsGraphView &g, int dc_inst, int dv_inst, int dmin, bool search, MsPlanLayout &L, int team_warps = 1, bool sub8 = false,
+                           bool packed = false)
 {
     const int n = g.n;
     L.dc_inst = dc_inst; L.dv_inst = dv_inst; L.dmin = dmin;
@@ -397,9 +405,9 @@ inline void ms_plan_layout(const MsGraphView &g, int dc_inst, int dv_inst, int d
         L.cnt[x] = 0;
         if (x < dv) for (int j = 0; j < n; ++j) L.cnt[x] += deg[j] > x;
         L.coff[x] = words;
-        if (x < dv_inst) words += sub8 ? ((L.cnt[x] + 7) & ~7) : ((L.cnt[x] + (x < dmin ? 1 : 0) + 31) & ~31);
+        if (x < dv_inst) words += sub8 ? ((L.cnt[x] + 7) & ~7) : (packed ? ((L.cnt[x] + (x < dmin ? 1 : 0) + 15) & ~15) : ((L.cnt[x] + (x < dmin ? 1 : 0) + 31) & ~31));
     }
-    L.c2v_words = words;
+    L.c2v_words = (words + 3) & ~3;
     L.edge_rank.assign(g.E, 0);
     {
         std::vector<int> fill(n, 0);

@@ -7,7 +7,8 @@
 extern "C" int ms_plan_probe(int m, int n, int E, const int *row_ptr, const int *col_idx, int nl, const int *layer_ptr,
                              const int *layer_chk, int dc_inst, int dv_inst, int dmin, int search,
                              int *perm_out /*[n]*/, int *slot_edge_out /*[m*dc_inst]*/, int *lvar_ptr_out /*[nl+1]*/,
-                             unsigned *lvar_out, int lvar_cap, long long *stats /*[6]: wavefronts, ideal, evals, c2v_words, lvar_len, baseline*/)
+                             unsigned *lvar_out, int lvar_cap, long long *stats /*[6]: wavefronts, ideal, evals, c2v_words, lvar_len, baseline*/,
+                             int packed)
 {
     std::vector<int> cw(n, 0), col_ptr(n + 1, 0), row_idx(E), fill(n, 0);
     for (int x = 0; x < E; ++x) cw[col_idx[x]]++;
@@ -16,8 +17,8 @@ extern "C" int ms_plan_probe(int m, int n, int E, const int *row_ptr, const int 
         for (int x = row_ptr[i]; x < row_ptr[i + 1]; ++x) row_idx[col_ptr[col_idx[x]] + fill[col_idx[x]]++] = i;
     qldpc::MsGraphView g{m, n, E, row_ptr, col_idx, col_ptr.data(), row_idx.data(), nl, layer_ptr, layer_chk};
     qldpc::MsPlanLayout base, L;
-    qldpc::ms_plan_layout(g, dc_inst, dv_inst, dmin, false, base);
-    qldpc::ms_plan_layout(g, dc_inst, dv_inst, dmin, search != 0, L);
+    qldpc::ms_plan_layout(g, dc_inst, dv_inst, dmin, false, base, 1, false, packed != 0);
+    qldpc::ms_plan_layout(g, dc_inst, dv_inst, dmin, search != 0, L, 1, false, packed != 0);
     std::memcpy(perm_out, L.perm.data(), sizeof(int) * n);
     std::memcpy(slot_edge_out, L.slot_edge.data(), sizeof(int) * (size_t)m * dc_inst);
     std::memcpy(lvar_ptr_out, L.lvar_ptr.data(), sizeof(int) * (nl + 1));

@@ -299,8 +299,16 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
         size_t state = 0;
         const void *fn = nullptr;
         if (is_ms) {
+          // Two passes at most: the tables are built with the regions of the c2v array on multiples of 32 words and the shot states
+          // 128 bytes apart; if the packed variant (16 words / 16 bytes) would hold more shots per SM, they are built again that way.
+          static const int packed_env = [] { const char *ev = getenv("QLDPC_MS_PACKED"); return ev ? atoi(ev) : -1; }();   // tuning knob: 0 / 1 force
+          bool packed = packed_env == 1;
+          for (int pass = 0; pass < 2; ++pass) {
+            b.clear();
             // ================= min-sum tables (layout described in ms_kernel.cuh, planned by ms_plan.h) =================
             MsTables &mt = pk->ms_tab;
+            mt = MsTables{};
+            pk->ms_sub = nullptr;
             if (dv > kMsMaxDv) return bail(QLDPC_ETOOBIG, "min-sum kernels are instantiated for row weight <= 32 and column weight <= 16");
             int full_regions = 0;      // leading regions that hold every variable: x < min column weight
             {
@@ -390,7 +398,8 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             }
             MsGraphView gv{m, n, E, p->row_ptr.data(), p->col_idx.data(), p->col_ptr.data(), p->row_idx.data(), nsteps, step_ptr.data(), p->layer_chk.data()};
             MsPlanLayout pl;
-            ms_plan_layout(gv, dc_inst, dv_inst, dmin, /*search=*/true, pl, W, /*sub8=*/use_sub);
+            const bool pk_regions = packed && !use_sub;
+            ms_plan_layout(gv, dc_inst, dv_inst, dmin, /*search=*/true, pl, W, /*sub8=*/use_sub, pk_regions);
             if (!use_sub && dmin > 0 && dmin < dv_inst && 100ll * pl.sub_total > 115ll * pl.sub_min) {
                 // the [low, low, any, any] quad pattern of the partially guarded instances needs too many padding sub-groups on this
                 // graph (few variables of degree <= dmin): use the instance that guards every region instead
@@ -399,7 +408,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
                 int a1, a2;
                 pk->ms = ms_select(dc, dv, 0, W == 2 ? 2 : 0, spec, &a1, &a2, &dmin);
                 pl = MsPlanLayout();
-                ms_plan_layout(gv, dc_inst, dv_inst, dmin, /*search=*/true, pl, W);
+                ms_plan_layout(gv, dc_inst, dv_inst, dmin, /*search=*/true, pl, W, false, pk_regions);
             }
             p->plan_wavefronts = pl.wavefronts; p->plan_wavefronts_ideal = pl.ideal;
             mt.m = m; mt.n = n; mt.E = E; mt.dc = dc_inst; mt.dv = dv; mt.nl = nsteps; mt.mw = t.mw; mt.nw = t.nw;
@@ -510,9 +519,24 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             b.resize((b.size() + 7) & ~size_t(7), 0);
             mt.len = (int)b.size();
             t.len = mt.len;
-            state = ms_layout(mt).bytes;
+            mt.packed = pk_regions ? 1 : 0;
+            state = pk_regions ? ms_layout(mt).bytes16 : ms_layout(mt).bytes;
             fn = (const void *)pk->ms;
             if (use_sub) { state = 4 * (size_t)ms_layout(mt).bytes16; fn = (const void *)pk->ms_sub; }      // a warp holds four interleaved shots
+            if (pass == 1 || packed || use_sub || packed_env == 0) break;
+            {   // would the packed variant hold more shots?  (same tables, hence the same blob size)
+                MsPlanLayout probe_pl;
+                ms_plan_layout(gv, dc_inst, dv_inst, dmin, /*search=*/false, probe_pl, W, false, true);
+                MsTables probe = mt;
+                probe.c2v_words = probe_pl.c2v_words;
+                const size_t st_packed = ms_layout(probe).bytes16, bb = (size_t)ms_table_bytes(mt);
+                if (bb + state > (size_t)kMaxSmemPerCta) break;
+                const size_t fit_now = ((size_t)kMaxSmemPerCta - bb) / state, fit_packed = ((size_t)kMaxSmemPerCta - bb) / st_packed;
+                const size_t cap = (size_t)(W > 1 ? std::min(kMsWarps / W, 15) : kMsWarpsBig);
+                if (std::min(fit_packed, cap) <= std::min(fit_now, cap)) break;
+                packed = true;
+            }
+          }
         } else {
             // ================= sum-product tables (slot-major edge layout, see common.cuh) =================
             // Slot stride of the binary64 c2v array.  lane = (check of the pass, slot): a stride of 4 (mod 16) puts the slots of the

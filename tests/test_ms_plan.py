@@ -32,7 +32,7 @@ def kernel_shape(H):
     return dci, dvi, dmin
 
 
-def run_planner(lib, H, layers, search=1):
+def run_planner(lib, H, layers, search=1, packed=0):
     c = pcm.compile_pcm(H, find_qc=False)
     lp, lc = pcm.flatten_layers(layers)
     m, n = H.shape
@@ -44,7 +44,7 @@ def run_planner(lib, H, layers, search=1):
     stats = np.zeros(6, np.int64)
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     rc = lib.ms_plan_probe(m, n, c.nnz, P(c.row_ptr), P(c.col_idx), len(layers), P(lp), P(lc), dci, dvi, dmin, search,
-                           P(perm), P(slot_edge), P(lvar_ptr), P(lvar), lvar.size, P(stats))
+                           P(perm), P(slot_edge), P(lvar_ptr), P(lvar), lvar.size, P(stats), packed)
     assert rc == 0
     return c, dci, perm, slot_edge.reshape(m, dci), lvar_ptr, lvar[:stats[4]], stats
 
@@ -133,3 +133,23 @@ def test_eight_lane_layout(planner, code):
         assert stats[1] <= stats[0] <= stats[3]
         if code == "bicycle":
             assert stats[3] > 1.4 * stats[1] and stats[0] <= 1.10 * stats[1], stats
+
+
+@pytest.mark.parametrize("code,sched", [("LP118_0", "L"), ("LP118_0", "F"), ("LP04_0", "L"), ("T", "L")])
+def test_packed_regions(planner, code, sched):
+    """Packed layout (regions of the c2v array on multiples of 16 instead of 32 words: the 21st resident shot of LP118_0): the
+    array shrinks or stays, every edge keeps exactly one slot, and the modelled shared-memory wavefronts -- the planner's bank
+    model follows the per-region rotation -- stay within 10 % of the aligned layout's."""
+    Hx, Hz = [(h % 2).astype(np.int8) for h in pcmlibrary.by_name(code)]
+    lX, lZ = pcm.schedule_layers(Hx, Hz, sched)
+    for H, layers in ((Hz, lX), (Hx, lZ)):
+        c, dci, perm0, se0, _, _, st0 = run_planner(planner, H, layers, 1, 0)
+        c, dci, perm1, se1, _, _, st1 = run_planner(planner, H, layers, 1, 1)
+        assert st1[3] <= st0[3] and st1[3] % 4 == 0
+        assert st1[0] <= 1.10 * st0[0]
+        assert sorted(perm1.tolist()) == list(range(H.shape[1]))
+        for i in range(H.shape[0]):
+            e = se1[i][se1[i] >= 0]
+            assert sorted(e.tolist()) == list(range(c.row_ptr[i], c.row_ptr[i + 1]))
+        if code == "LP118_0":
+            assert st0[3] == 2048 and st1[3] == 1968
