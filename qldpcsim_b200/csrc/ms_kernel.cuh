@@ -129,6 +129,7 @@ __device__ __forceinline__ float sld_f32(uint32_t a) { float v; asm volatile("ld
 __device__ __forceinline__ uint32_t sld_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t sld_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sst_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sst_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((unsigned short)v) : "memory"); }
 __device__ __forceinline__ void sst_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sred_xor(uint32_t a, uint32_t v) { asm volatile("red.shared.xor.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t satom_xor(uint32_t a, uint32_t v) { uint32_t o; asm volatile("atom.shared.xor.b32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o; }
@@ -139,6 +140,7 @@ struct MsAddr {          // shared-window byte addresses, warp-uniform
     uint32_t col_chk;
     uint32_t c2v, S, par, syn;   // per-warp state
     uint32_t m4;         // 4*ms : byte stride of one slot row in chk
+    uint32_t list;       // 16 bytes of per-warp scratch: the flipped variables of a quad trip (one-warp teams; the team box otherwise unused)
 };
 
 // Check-node phase of one layer with LPC lanes per check (decoders.py:156-169).
@@ -301,9 +303,41 @@ __device__ __forceinline__ void ms_var_update1(uint32_t ja4, int lane, const MsA
     if (fa) ms_apply_flips<DV>(fa, ja4, lane, A, delta);
 }
 
+// All flipped variables of a quad trip in ONE pass (one-warp teams).  More than half of all quad trips see a flip (the shots that
+// never converge oscillate through all max_iter iterations), 2.3 flipped variables on average, and the cooperative loop above
+// spends a shuffle -> load -> atomic round trip and ~25 instructions on each.  Here every flipping lane drops its variable into a
+// short list (slot = number of flips before it, from the ballots), and lane 5q + x (DV = 5) toggles the x-th check of the q-th
+// listed variable: up to 32 / DV flips (at most 8) per pass, whatever their number; longer lists take the loop.
+template <int DV>
+__device__ __forceinline__ bool ms_apply_flips_compact(const uint32_t (&f)[4], const uint32_t (&j4)[4], int lane, const MsAddr &A, int &delta)
+{
+    constexpr int CAP = (32 / DV) < 8 ? (32 / DV) : 8;
+    const int c0 = __popc(f[0]), c1 = c0 + __popc(f[1]), c2 = c1 + __popc(f[2]), F = c2 + __popc(f[3]);
+    if (F > CAP) return false;
+    const uint32_t lt = (1u << lane) - 1u;
+    if ((f[0] >> lane) & 1u) sst_u16(A.list + 2u * (uint32_t)__popc(f[0] & lt), j4[0]);
+    if ((f[1] >> lane) & 1u) sst_u16(A.list + 2u * (uint32_t)(c0 + __popc(f[1] & lt)), j4[1]);
+    if ((f[2] >> lane) & 1u) sst_u16(A.list + 2u * (uint32_t)(c1 + __popc(f[2] & lt)), j4[2]);
+    if ((f[3] >> lane) & 1u) sst_u16(A.list + 2u * (uint32_t)(c2 + __popc(f[3] & lt)), j4[3]);
+    __syncwarp();
+    const int q = lane / DV, x = lane - q * DV;
+    if (q < F) {
+        const uint32_t jf4 = sld_u16(A.list + 2u * (uint32_t)q);
+        const uint32_t ch = sld_u16(A.col_chk + (jf4 >> 1) * (uint32_t)DV + 2u * (uint32_t)x);
+        if (ch != 0xffffu) {
+            const uint32_t bit = 1u << (ch & 31u);
+            const uint32_t old = satom_xor(A.par + 4u * (ch >> 5), bit);
+            delta += (old & bit) ? -1 : 1;
+        }
+    }
+    __syncwarp();                                                             // the list is rewritten by the next flipping trip
+    return true;
+}
+
 // Same with FOUR variables per lane (two consecutive pair-trips of the layer's list at once): more independent chains in
-// flight and half the loop overhead for the common layers whose variables fill four sub-groups.
-template <int DV, int DMIN>
+// flight and half the loop overhead for the common layers whose variables fill four sub-groups.  COMPACT: one-warp teams
+// without merged steps handle the flips of the trip in one pass (ms_apply_flips_compact).
+template <int DV, int DMIN, bool COMPACT>
 __device__ __forceinline__ void ms_var_update4(uint32_t e0, uint32_t e1, int lane, const MsAddr &A, const MsTables &t, float Tf, int &delta)
 {
     const uint32_t j4[4] = {e0 & 0xffffu, e0 >> 16, e1 & 0xffffu, e1 >> 16};
@@ -318,6 +352,7 @@ __device__ __forceinline__ void ms_var_update4(uint32_t e0, uint32_t e1, int lan
         f[v] = __ballot_sync(0xffffffffu, (s[v] < Tf) != (s_old[v] < Tf));      // hard decision flipped (:173-174)
     }
     if (f[0] | f[1] | f[2] | f[3]) {
+        if constexpr (COMPACT) { if (ms_apply_flips_compact<DV>(f, j4, lane, A, delta)) return; }
 #pragma unroll
         for (int v = 0; v < 4; ++v) ms_apply_flips<DV>(f[v], j4[v], lane, A, delta);
     }
@@ -365,6 +400,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
     A.par = wbase + lay.off_par;
     A.syn = wbase + lay.off_syn;
     A.m4 = 4u * t.ms;
+    A.list = team_box;
     const uint32_t layer_rec = tab + 2u * t.off_layer, lvar = tab + 2u * t.off_lvar, lsub = tab + 2u * t.off_lsub;
     const uint32_t rowpar = tab + 2u * t.off_rowpar, unperm = tab + 2u * t.off_unperm;
     const int n = t.n;
@@ -541,7 +577,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
                 int delta = 0;
                 for (int p = 2 * sub; p + 1 < P; p += 2 * W) {
                     const int q = vb + 32 * p + lane;
-                    ms_var_update4<DV, DMIN>(sld_u32(lvar + 4u * q), sld_u32(lvar + 4u * q + 128u), lane, A, t, Tf, delta);
+                    ms_var_update4<DV, DMIN, (W == 1 && !SPEC)>(sld_u32(lvar + 4u * q), sld_u32(lvar + 4u * q + 128u), lane, A, t, Tf, delta);
                 }
                 if ((P & 1) && ((P >> 1) % W) == sub) {                        // odd pair-trip at the end
                     const uint32_t e = sld_u32(lvar + 4u * (uint32_t)(ve - 32 + lane));
