@@ -86,6 +86,7 @@ struct MsTables {
     int off_rowpar;      // u32 [mw]      parity of the row weights as bit words
     int off_unperm;      // u16 [32*nw]   4*j' of original variable j (4*n past the end)
     int len;             // blob length in uint16 units (multiple of 8)
+    int team;            // warps per shot (multi-warp teams get 16 bytes of flip-list scratch per warp behind the team box)
     int packed;          // 1: regions rounded to 16 words and shot states 16 bytes apart (ms_plan.h: packed), 0: 32 words / 128 bytes
     int cnt4[kMsMaxDv];  // 4 * number of variables of degree > x
     int coff4[kMsMaxDv]; // byte offset of region x in the c2v array
@@ -117,6 +118,7 @@ __host__ __device__ inline MsSmemLayout ms_layout(const MsTables &t)
     l.off_syn = o; o += 4 * t.mw;
     o = (o + 7) & ~7;
     l.off_team = o; o += 16;
+    if (t.team > 1) o += 16 * t.team;     // per-warp flip lists (a one-warp team uses its otherwise idle team box)
     l.bytes = (o + 127) & ~127;
     l.bytes16 = (o + 15) & ~15;
     return l;
@@ -140,7 +142,7 @@ struct MsAddr {          // shared-window byte addresses, warp-uniform
     uint32_t col_chk;
     uint32_t c2v, S, par, syn;   // per-warp state
     uint32_t m4;         // 4*ms : byte stride of one slot row in chk
-    uint32_t list;       // 16 bytes of per-warp scratch: the flipped variables of a quad trip (one-warp teams; the team box otherwise unused)
+    uint32_t list;       // 16 bytes of per-warp scratch: the flipped variables of a quad trip
 };
 
 // Check-node phase of one layer with LPC lanes per check (decoders.py:156-169).
@@ -307,7 +309,8 @@ __device__ __forceinline__ void ms_var_update1(uint32_t ja4, int lane, const MsA
 // never converge oscillate through all max_iter iterations), 2.3 flipped variables on average, and the cooperative loop above
 // spends a shuffle -> load -> atomic round trip and ~25 instructions on each.  Here every flipping lane drops its variable into a
 // short list (slot = number of flips before it, from the ballots), and lane 5q + x (DV = 5) toggles the x-th check of the q-th
-// listed variable: up to 32 / DV flips (at most 8) per pass, whatever their number; longer lists take the loop.
+// listed variable: up to 32 / DV flips (at most 8) per pass, whatever their number; longer lists take the loop.  The list is
+// per warp (A.list): a one-warp team uses its idle team box, the warps of a larger team 16 bytes each behind it.
 template <int DV>
 __device__ __forceinline__ bool ms_apply_flips_compact(const uint32_t (&f)[4], const uint32_t (&j4)[4], int lane, const MsAddr &A, int &delta)
 {
@@ -400,7 +403,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
     A.par = wbase + lay.off_par;
     A.syn = wbase + lay.off_syn;
     A.m4 = 4u * t.ms;
-    A.list = team_box;
+    A.list = W == 1 ? team_box : team_box + 16u + 16u * (uint32_t)sub;
     const uint32_t layer_rec = tab + 2u * t.off_layer, lvar = tab + 2u * t.off_lvar, lsub = tab + 2u * t.off_lsub;
     const uint32_t rowpar = tab + 2u * t.off_rowpar, unperm = tab + 2u * t.off_unperm;
     const int n = t.n;
@@ -537,7 +540,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
 #pragma unroll
                         for (int v = 0; v < 4; ++v) sst_f32(A.S + j4[v], s_new[v]);
                         int delta = 0;
-                        if (F) {
+                        if (F && !ms_apply_flips_compact<DV>(f, j4, lane, A, delta)) {
 #pragma unroll
                             for (int v = 0; v < 4; ++v) ms_apply_flips<DV>(f[v], j4[v], lane, A, delta);
                         }
@@ -577,7 +580,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
                 int delta = 0;
                 for (int p = 2 * sub; p + 1 < P; p += 2 * W) {
                     const int q = vb + 32 * p + lane;
-                    ms_var_update4<DV, DMIN, (W == 1 && !SPEC)>(sld_u32(lvar + 4u * q), sld_u32(lvar + 4u * q + 128u), lane, A, t, Tf, delta);
+                    ms_var_update4<DV, DMIN, true>(sld_u32(lvar + 4u * q), sld_u32(lvar + 4u * q + 128u), lane, A, t, Tf, delta);
                 }
                 if ((P & 1) && ((P >> 1) % W) == sub) {                        // odd pair-trip at the end
                     const uint32_t e = sld_u32(lvar + 4u * (uint32_t)(ve - 32 + lane));

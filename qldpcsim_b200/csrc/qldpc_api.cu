@@ -520,6 +520,7 @@ int qldpc_plan_create(const qldpc_graph *g, const qldpc_opts *o, int device, qld
             mt.len = (int)b.size();
             t.len = mt.len;
             mt.packed = pk_regions ? 1 : 0;
+            mt.team = W;
             state = pk_regions ? ms_layout(mt).bytes16 : ms_layout(mt).bytes;
             fn = (const void *)pk->ms;
             if (use_sub) { state = 4 * (size_t)ms_layout(mt).bytes16; fn = (const void *)pk->ms_sub; }      // a warp holds four interleaved shots
