@@ -338,9 +338,9 @@ __device__ __forceinline__ bool ms_apply_flips_compact(const uint32_t (&f)[4], c
 }
 
 // Same with FOUR variables per lane (two consecutive pair-trips of the layer's list at once): more independent chains in
-// flight and half the loop overhead for the common layers whose variables fill four sub-groups.  COMPACT: one-warp teams
-// without merged steps handle the flips of the trip in one pass (ms_apply_flips_compact).
-template <int DV, int DMIN, bool COMPACT>
+// flight and half the loop overhead for the common layers whose variables fill four sub-groups.  The flips of the trip are
+// handled in one pass (ms_apply_flips_compact) unless there are more than it takes.
+template <int DV, int DMIN>
 __device__ __forceinline__ void ms_var_update4(uint32_t e0, uint32_t e1, int lane, const MsAddr &A, const MsTables &t, float Tf, int &delta)
 {
     const uint32_t j4[4] = {e0 & 0xffffu, e0 >> 16, e1 & 0xffffu, e1 >> 16};
@@ -355,7 +355,7 @@ __device__ __forceinline__ void ms_var_update4(uint32_t e0, uint32_t e1, int lan
         f[v] = __ballot_sync(0xffffffffu, (s[v] < Tf) != (s_old[v] < Tf));      // hard decision flipped (:173-174)
     }
     if (f[0] | f[1] | f[2] | f[3]) {
-        if constexpr (COMPACT) { if (ms_apply_flips_compact<DV>(f, j4, lane, A, delta)) return; }
+        if (ms_apply_flips_compact<DV>(f, j4, lane, A, delta)) return;
 #pragma unroll
         for (int v = 0; v < 4; ++v) ms_apply_flips<DV>(f[v], j4[v], lane, A, delta);
     }
@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
                 int delta = 0;
                 for (int p = 2 * sub; p + 1 < P; p += 2 * W) {
                     const int q = vb + 32 * p + lane;
-                    ms_var_update4<DV, DMIN, true>(sld_u32(lvar + 4u * q), sld_u32(lvar + 4u * q + 128u), lane, A, t, Tf, delta);
+                    ms_var_update4<DV, DMIN>(sld_u32(lvar + 4u * q), sld_u32(lvar + 4u * q + 128u), lane, A, t, Tf, delta);
                 }
                 if ((P & 1) && ((P >> 1) % W) == sub) {                        // odd pair-trip at the end
                     const uint32_t e = sld_u32(lvar + 4u * (uint32_t)(ve - 32 + lane));
