@@ -597,10 +597,23 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
         const int iters = (converged && it == 0) ? 1 : it;
         edges_done += shot_edges;
         // ---- outputs: e_j = (S_j' < Tf)
-        for (int w = sub; w < t.nw; w += W) {
-            const int j = w * 32 + lane;
-            const uint32_t bits = __ballot_sync(full, j < n && c.max_iter > 0 && sld_f32(A.S + sld_u16(unperm + 2u * j)) < Tf);
-            if (lane == 0) io.ehat[shot * t.nw + w] = bits;
+        // (the k-th word a warp forms stays in lane k mod 32; one coalesced store per 32 words instead of one store, with its
+        // 64-bit address arithmetic, per word: the loop is 4 % of the kernel's instructions otherwise)
+        {
+            uint32_t *erow = io.ehat + shot * t.nw;
+            uint32_t mine = 0;
+            int k = 0;
+            for (int w = sub; w < t.nw; w += W, ++k) {
+                const int j = w * 32 + lane;
+                const uint32_t bits = __ballot_sync(full, j < n && c.max_iter > 0 && sld_f32(A.S + sld_u16(unperm + 2u * j)) < Tf);
+                if (lane == (k & 31)) mine = bits;
+                if ((k & 31) == 31) {                                       // rows of more than 32 words per warp
+                    erow[sub + (k - 31 + lane) * W] = mine;
+                    mine = 0;
+                }
+            }
+            const int rest = k & 31, k0 = k - rest;
+            if (lane < rest) erow[sub + (k0 + lane) * W] = mine;
         }
         if (tl == 0) {
             io.iters[shot] = iters;
