@@ -460,31 +460,25 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ms_decode_kernel(MsTables t, con
         bool converged = false;
         int it = 0;
         uint32_t shot_edges = 0;
-        if (c.max_iter > 0) {
-            shot_edges = sld_u16(layer_rec + 14u);
-            // ---------------- first layer step: prior is the binary32-rounded L (decoders.py:148-149) and the variable
-            // phase visits EVERY variable (the reference recomputes all posteriors; a variable outside layer 0 has
-            // posterior L, which may be negative for p > 1/2)
-            const int qb = sld_u16(layer_rec), qe = sld_u16(layer_rec + 2u);
-            ms_check_phase<DC, 1>(qb, qe, sub, W, lane, A, c.Lf, c.abeta, c.sgn);
-            team_sync();
-            int delta = 0;
-            for (int q = 64 * sub + lane; q < t.n_pad; q += 64 * W)
-                ms_var_update2<DV, DMIN>(q < n ? 4u * q : n4, q + 32 < n ? 4u * (q + 32) : n4, lane, A, t, Tf, delta);
-            settle(delta);
-            converged = unsat == 0;
+        {
+            // The first layer step of a shot is an ordinary step whose prior is the binary32-rounded L (decoders.py:148-149).  The
+            // reference recomputes the posterior of EVERY variable after it; a variable outside layer 0 has no message yet, its sum
+            // stays 0 and its decision (0 < Tf, i.e. L < 0: p > 1/2) is the one the initial residual already assumes, so only the
+            // variables of layer 0 need a visit -- the sweep over all n variables this kernel used to make cost 7 % of its
+            // instructions.
         }
         for (; it < c.max_iter && !converged; ++it) {
-            for (int l = (it == 0 ? 1 : 0); l < t.nl; ++l) {
+            for (int l = 0; l < t.nl; ++l) {
                 // ---------------- check-node phase (decoders.py:156-169)
+                const double prior = (it == 0 && l == 0) ? c.Lf : c.L;
                 uint32_t r0, r1, r2, r3;                                       // the layer's 16-byte record
                 asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(layer_rec + 16u * l));
                 const int qb = r0 & 0xffffu, qe = r0 >> 16, lpc = r1 & 0xffffu;
                 shot_edges += r3 >> 16;
-                if (lpc == 1) ms_check_phase<DC, 1>(qb, qe, sub, W, lane, A, c.L, c.abeta, c.sgn);
-                else if (lpc == 2) ms_check_phase<DC, 2>(qb, qe, sub, W, lane, A, c.L, c.abeta, c.sgn);
-                else if (lpc == 4) ms_check_phase<DC, 4>(qb, qe, sub, W, lane, A, c.L, c.abeta, c.sgn);
-                else if constexpr (DC % 8 == 0) ms_check_phase<DC, 8>(qb, qe, sub, W, lane, A, c.L, c.abeta, c.sgn);   // DC = 4: lpc <= 4
+                if (lpc == 1) ms_check_phase<DC, 1>(qb, qe, sub, W, lane, A, prior, c.abeta, c.sgn);
+                else if (lpc == 2) ms_check_phase<DC, 2>(qb, qe, sub, W, lane, A, prior, c.abeta, c.sgn);
+                else if (lpc == 4) ms_check_phase<DC, 4>(qb, qe, sub, W, lane, A, prior, c.abeta, c.sgn);
+                else if constexpr (DC % 8 == 0) ms_check_phase<DC, 8>(qb, qe, sub, W, lane, A, prior, c.abeta, c.sgn);   // DC = 4: lpc <= 4
                 team_sync();
                 // ---------------- variable-node phase (decoders.py:172-174) on the variables whose sums changed.  Every
                 // lane runs the same number of trips (lists are padded to whole trips with the dummy variable n).
