@@ -32,8 +32,12 @@
 //     double sum of two doubles is exact whenever it is tiny, so its sign is the sign of the real sum), which
 //     needs one binary32 compare and no stored decision bits: the previous decision is S_j(old) < Tf;
 //   * convergence is tested after every layer step (decoders.py:175-176) on an incrementally maintained count
-//     of unsatisfied checks: a flipped decision toggles the parity bits of its checks (shared-memory atomics,
-//     rare) and adds +-1 per toggled bit;
+//     of unsatisfied checks: a flipped decision toggles the parity bits of its checks (shared-memory atomics)
+//     and adds +-1 per toggled bit.  Flips are NOT rare -- the shots that never converge oscillate through all
+//     max_iter iterations and own a sixth of all steps on LP118_0 at p = 0.05: more than half of all quad trips
+//     see one -- so all flipped variables of a quad trip are handled in one pass (ms_apply_flips_compact);
+//   * the first layer step of a shot is an ordinary step whose prior is the binary32-rounded L: variables outside
+//     layer 0 have no message yet, their sum stays 0 and their decision is the one the initial residual assumes;
 //   * MERGED STEPS (SPEC instances).  Consecutive layers whose variable sets are pairwise disjoint -- the single-check layers of
 //     the serial schedule inside one circulant block row, simulator.py:228-236 'S' -- read nothing that an earlier layer of the
 //     run writes, so their check phases and variable phases are executed as ONE step (the plan builder forms the runs).  What
