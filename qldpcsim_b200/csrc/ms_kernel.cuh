@@ -73,7 +73,7 @@ struct MsTables {
     int nl;              // layers
     int mw, nw;          // words(m), words(n)
     int ms;              // row stride of chk (>= m; ms = 4 mod 8 keeps the lane groups of a split check on disjoint banks)
-    int n_pad;           // n rounded up to a multiple of 64 (first-step sweep: two variables per lane and trip)
+    int n_pad;           // n rounded up to a multiple of 64 (no longer read by the kernels: the first layer step is an ordinary step)
     int c2v_words;       // words of the per-shot c2v array (regions start on multiples of 32 words -- bank 0 -- or, packed, of 16)
     int off_chk;         // u32 [dc*ms]   lo16 = 4*j' (byte offset of S_j'), hi16 = byte offset of the edge's c2v word.  Slots past the
                          //               end of a short row hold a PADDING EDGE: S entry n+1 (always +inf) and the scratch word S[n+2]
